@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the reverse-diffusion scoring path (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this implementation (CUDA)
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference algorithm on host cores
+
+One "step" = one pass of the hot path (the body of MoCoDAD.forward, models/mocodad.py:129-184) over
+one batch of synthetic windows: B windows/GPU of [2, seg_len=27, 17] (3 conditioning + T=24 denoised
+frames, BASELINE.json's [B,2,24,17] shape), noise_steps=10 (9 denoiser calls), n_generated_samples=50,
+'best' aggregation, SmoothL1 -- i.e. 450 window-steps per window.  Weights: random "trained-looking"
+checkpoint (no checkpoints ship with the reference).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "skeleton_windows_per_sec_full_reverse_diffusion"
+UNIT = "windows/s"
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--batch", type=int, default=1024, help="windows per GPU per step")
+    p.add_argument("--seg-len", type=int, default=27)
+    p.add_argument("--noise-steps", type=int, default=10)
+    p.add_argument("--gen", type=int, default=50, help="n_generated_samples")
+    p.add_argument("--cpu-sample", default="128x5", help="cpu_baseline sample: windows x samples")
+    p.add_argument("--ref-sample", default="32x5", help="--impl reference: windows x samples per step")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def workload_config(a):
+    T = a.seg_len - 3
+    return {"workload": f"synthetic windows [B,2,{T},17] (seg_len {a.seg_len}, 3 conditioning frames, 'inject'), "
+                        f"noise_steps={a.noise_steps}, n_generated_samples={a.gen}, best-of-n SmoothL1 "
+                        "(BASELINE.json configs[1] shape)",
+            "windows_per_gpu_per_step": a.batch, "seg_len": a.seg_len, "T": T, "V": 17,
+            "noise_steps": a.noise_steps, "n_generated_samples": a.gen,
+            "window_steps_per_window": a.gen * (a.noise_steps - 1),
+            "cache": "per-step working set (activations of a >2000-window tile, ~0.9 GB) exceeds the 126 MB L2; "
+                     "fresh Philox noise every step"}
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_reference_rate(a, n_windows: int, n_samples: int, steps: int, warmup: int):
+    """Times oracle/ref_port.py (the reference's PyTorch operators, CPU) on a bounded sample of the
+    workload; returns (equivalent windows/s at the workload's n_generated_samples, seconds/step)."""
+    from oracle import ref_port, synth
+    T = a.seg_len - 3
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.synth_state_dict(synth.state_dict_spec(T=T, T_cond=3), seed=0)
+    data = synth.synth_batch(n_windows, a.seg_len, seed=1)[0]
+    gen = torch.Generator().manual_seed(999)
+
+    def one():
+        with torch.no_grad():
+            ref_port.reverse_diffusion(sd, data, noise_steps=a.noise_steps, n_generated_samples=n_samples,
+                                       randn_like=lambda x: torch.randn(x.shape, generator=gen))
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    window_steps_per_s = n_windows * n_samples * (a.noise_steps - 1) / dt
+    return window_steps_per_s / (a.gen * (a.noise_steps - 1)), dt
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nw, ns = (int(x) for x in a.ref_sample.split("x"))
+    value, dt = cpu_reference_rate(a, nw, ns, a.steps, a.warmup)
+    cores = os.cpu_count() or 1
+    sample = (f"{nw} windows x {ns} samples x {a.noise_steps - 1} denoiser calls per step on the host CPU; rate scaled "
+              f"to the workload's {a.gen} samples/window (window-steps are identical work)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- CUDA arm
+def run_b200(a):
+    import torch.distributed as dist
+    from mocodad_b200 import ScoringEngine
+    from mocodad_b200.engine import probe_fp32_tflops
+    from oracle import synth  # synthetic checkpoint / windows generator (inputs only, nothing is computed with it)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the scoring path has no CPU implementation (use --impl reference "
+                         "for the host-core baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    T = a.seg_len - 3
+    B, G, N = a.batch, a.gen, a.noise_steps
+    eng = ScoringEngine(seg_len=a.seg_len, n_frames_cond=3, noise_steps=N, device=dev)
+    eng.load_state_dict(synth.synth_state_dict(synth.state_dict_spec(T=T, T_cond=3), seed=0))
+    host = synth.synth_batch(B, a.seg_len, seed=1 + rank)[0].pin_memory()
+    data = host.to(dev)
+    first = rank * B  # this rank's windows in the global index space (weak scaling: B windows per rank)
+    step_no = [0]
+
+    def step_device():
+        res = eng.reverse_diffusion(data, G, seed=999, first_window=first + step_no[0] * world * B)
+        step_no[0] += 1
+        return res["best"]
+
+    def step_host():
+        out = eng.score_windows_host(host, G, seed=999, first_window=first + step_no[0] * world * B)
+        step_no[0] += 1
+        return out
+
+    # ---- value: inputs resident in HBM, device-timed --------------------------------------
+    for _ in range(a.warmup):
+        step_device()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = eng.launch_count()
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(a.steps):
+            best = step_device()
+        ev1.record()
+        barrier()
+    launches = eng.launch_count() - launches0
+    ms = max_over_ranks(ev0.elapsed_time(ev1)) / a.steps
+    value = world * B / (ms * 1e-3)
+    assert bool(torch.isfinite(best).all())
+
+    # ---- e2e: host buffers through the C-ABI host entry (H2D + loop + D2H + sync per step) ----
+    for _ in range(min(a.warmup, 2)):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        scores = step_host()
+    torch.cuda.synchronize(dev)
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / a.steps
+    barrier()
+    e2e_value = world * B / e2e_s
+    assert bool(torch.isfinite(scores).all())
+
+    # ---- per-kernel device times (CUDA events around every launch, one extra step) -----------
+    eng.profile_enable(True)
+    step_device()
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    total_ms = sum(v["ms"] for v in prof.values())
+    kernels = []
+    for name, v in prof.items():
+        if v["launches"] == 0:
+            continue
+        sec = v["ms"] * 1e-3
+        kernels.append({"kernel": name, "launches": v["launches"], "ms": round(v["ms"], 3),
+                        "share": round(v["ms"] / total_ms, 4),
+                        "GBps": round(v["bytes_per_window"] * v["windows"] / sec / 1e9, 1),
+                        "TFLOPs": round(v["flops_per_window"] * v["windows"] / sec / 1e12, 2)})
+    kernels.sort(key=lambda k: -k["ms"])
+    top = kernels[0]
+    pv = prof[top["kernel"]]
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        hbm_peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    fp32_peak = probe_fp32_tflops(local)
+    top_sec_per_launch = pv["ms"] * 1e-3 / pv["launches"]
+    top_bytes_per_launch = pv["bytes_per_window"] * pv["windows"] / pv["launches"]
+    top_flops_per_launch = pv["flops_per_window"] * pv["windows"] / pv["launches"]
+    achieved = top_bytes_per_launch / top_sec_per_launch / 1e9
+    per_call = [k for k in prof if k.startswith("st_gcnn") or k in ("down1", "down2", "up3", "up2", "ddpm_step")]
+    unet_flops = sum(prof[k]["flops_per_window"] for k in per_call)  # one denoiser call + DDPM update, per window
+    roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                "us_per_launch": round(top_sec_per_launch * 1e6, 1),
+                "algorithmic_bytes_per_launch": top_bytes_per_launch,
+                "note": "the path is fp32-FMA-bound, not HBM-bound (SURVEY.md 8d): see 'fp32'",
+                "fp32": {"achieved_tflops": round(top_flops_per_launch / top_sec_per_launch / 1e12, 2),
+                         "peak_tflops": round(fp32_peak, 2), "peak_source": "mcd_probe_fp32_tflops (FFMA loop, this GPU)",
+                         "frac": round(top_flops_per_launch / top_sec_per_launch / 1e12 / fp32_peak, 4),
+                         "whole_step_tflops": round(B * G * (N - 1) * unet_flops / (ms * 1e-3) / 1e12, 2)}}
+
+    cpu_baseline = None
+    if world == 1 and not a.no_cpu_baseline:
+        nw, ns = (int(x) for x in a.cpu_sample.split("x"))
+        cv, cdt = cpu_reference_rate(a, nw, ns, steps=1, warmup=1)
+        cpu_baseline = {"value": cv, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                        "sample": f"oracle/ref_port.py (the reference's torch CPU operators): {nw} windows x {ns} samples x "
+                                  f"{N - 1} steps in {cdt:.1f} s, scaled to {G} samples/window"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(a),
+            "window_steps_per_sec": value * G * (N - 1),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": B * 4,
+                    "ms_per_step": e2e_s * 1e3, "api": "mcd_score_windows_host (pinned host windows in, host scores out)"},
+            "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "kernels": kernels[:8]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

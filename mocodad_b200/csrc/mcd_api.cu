@@ -1,0 +1,1083 @@
+// mcd_api.cu -- host side of the C ABI declared in include/mocodad_b200.h.
+//
+// Weight packing (BatchNorm folding, layout changes), workspace carving, kernel dispatch and the
+// reverse-diffusion loop itself (the body of MoCoDAD.forward, models/mocodad.py:129-184).
+// No torch, no allocation on the compute path; every failure is reported, nothing falls back.
+#include "../../include/mocodad_b200.h"
+#include "mcd_kernels.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace mcd;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess) return fail(MCD_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+#define MCD_TRY(expr)          \
+  do {                         \
+    int rc_ = (expr);          \
+    if (rc_ != MCD_OK) return rc_; \
+  } while (0)
+
+// ---- the fixed architecture of the denoiser (models/stsae/stsae_unet.py:11,14,62-150,229-357) ----
+constexpr int kNumUnetBlocks = 11;
+constexpr int kNumResample = 4;
+constexpr int kNumEncBlocks = 4;
+struct BlockShape { const char* name; int cin, cout, level; };
+constexpr BlockShape kUnetBlocks[kNumUnetBlocks] = {
+    {"st_gcnnsp1a.0", 2, 16, 0},  {"st_gcnnsd1.0", 16, 32, 0},  {"st_gcnnsd1.1", 32, 32, 0},
+    {"st_gcnnsd2.0", 32, 64, 1},  {"st_gcnnsd2.1", 64, 64, 1},  {"st_gcnnsd3.0", 64, 128, 2},
+    {"st_gcnnsd3.1", 128, 64, 2}, {"st_gcnnsu4.0", 64, 64, 1},  {"st_gcnnsu4.1", 64, 32, 1},
+    {"st_gcnnsu3.0", 32, 32, 0},  {"st_gcnnsu3.1", 32, 2, 0}};
+constexpr int kPyramid[3] = {17, 12, 10};
+struct ResampleShape { const char* name; int lin, lout; };
+constexpr ResampleShape kResample[kNumResample] = {{"down1", 0, 1}, {"down2", 1, 2}, {"up3", 2, 1}, {"up2", 1, 0}};
+
+// profile / launch-count slots
+enum Slot {
+  SLOT_UNET0 = 0,                       // 11 ST_GCNN blocks of the denoiser
+  SLOT_RS0 = SLOT_UNET0 + kNumUnetBlocks,  // down1, down2, up3, up2
+  SLOT_DDPM = SLOT_RS0 + kNumResample,
+  SLOT_RANDN,
+  SLOT_LOSS,
+  SLOT_BEST,
+  SLOT_ENC0,                            // 4 ST_GCNN blocks of the conditioning encoder
+  SLOT_BTLNK = SLOT_ENC0 + kNumEncBlocks,
+  SLOT_TAP,
+  SLOT_COUNT
+};
+const char* kSlotNames[SLOT_COUNT] = {
+    "st_gcnnsp1a.0", "st_gcnnsd1.0", "st_gcnnsd1.1", "st_gcnnsd2.0", "st_gcnnsd2.1", "st_gcnnsd3.0",
+    "st_gcnnsd3.1",  "st_gcnnsu4.0", "st_gcnnsu4.1", "st_gcnnsu3.0", "st_gcnnsu3.1", "down1",
+    "down2",         "up3",          "up2",          "ddpm_step",    "randn",        "window_loss",
+    "best_worst",    "cond.enc0",    "cond.enc1",    "cond.enc2",    "cond.enc3",    "cond.btlnk",
+    "tap_transpose"};
+
+constexpr int nw_for(int T, int V0) {  // windows per CTA tile: ~408 (frame,joint) rows at the widest level
+  return (408 / (T * V0)) > 0 ? 408 / (T * V0) : 1;
+}
+
+struct PackedBlock {
+  int cin = 0, cout = 0, V = 0, T = 0;
+  bool emb = false, resconv = false;
+  BlockWeights w{};
+};
+struct PackedResample {
+  int vin = 0, vout = 0;
+  const float* W = nullptr;
+  const float* b = nullptr;
+};
+
+struct ProfEvent { cudaEvent_t a, b; int slot; int64_t windows; };
+
+}  // namespace
+
+struct mcd_model {
+  mcd_config cfg{};
+  int T = 0, Tc = 0, t0_corrupt = 0, t0_cond = 0, E = 0, N = 0;
+  int num_sms = 0;
+  bool finalized = false;
+  std::map<std::string, std::vector<float>> tensors;
+  float* d_arena = nullptr;
+  size_t arena_floats = 0;
+  PackedBlock unet[kNumUnetBlocks];
+  PackedBlock enc[kNumEncBlocks];
+  PackedResample rs[kNumResample];
+  const float* d_btl_W = nullptr;
+  const float* d_btl_b = nullptr;
+  const float* d_pos = nullptr;  // [N][E]
+  std::vector<float> beta, alpha, alpha_hat;
+  // per-window workspace (floats)
+  size_t ws_buf = 0, ws_d1 = 0, ws_d2 = 0, ws_x = 0;
+  // measurement
+  mutable std::atomic<int64_t> launches{0};
+  mutable bool prof_on = false;
+  mutable std::vector<ProfEvent> prof_events;
+  mutable size_t prof_used = 0;
+  mutable double prof_ms[SLOT_COUNT] = {};
+  mutable int64_t prof_launches[SLOT_COUNT] = {};
+  mutable int64_t prof_windows[SLOT_COUNT] = {};
+  // host-entry scratch
+  cudaStream_t own_stream = nullptr;
+  float* d_host_data = nullptr;
+  float* d_host_best = nullptr;
+  void* d_host_ws = nullptr;
+  size_t host_data_floats = 0, host_best_floats = 0, host_ws_bytes = 0;
+};
+
+namespace {
+
+// ---- launch bookkeeping ----------------------------------------------------------------------
+struct LaunchScope {
+  const mcd_model* m;
+  cudaStream_t s;
+  ProfEvent* ev = nullptr;
+  LaunchScope(const mcd_model* m_, int slot, int64_t windows, cudaStream_t s_) : m(m_), s(s_) {
+    m->launches.fetch_add(1, std::memory_order_relaxed);
+    if (m->prof_on) {
+      if (m->prof_used == m->prof_events.size()) {
+        ProfEvent e{};
+        if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
+        m->prof_events.push_back(e);
+      }
+      ev = &m->prof_events[m->prof_used++];
+      ev->slot = slot;
+      ev->windows = windows;
+      cudaEventRecord(ev->a, s);
+    }
+  }
+  ~LaunchScope() {
+    if (ev) cudaEventRecord(ev->b, s);
+  }
+};
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MCD_ERR_CUDA, "launch %s: %s", what, cudaGetErrorString(e));
+  return MCD_OK;
+}
+
+int grid_for(int64_t work_items, int per_cta, int num_sms, int waves) {
+  int64_t g = (work_items + per_cta - 1) / per_cta;
+  int64_t cap = int64_t(num_sms) * waves;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return int(g);
+}
+
+// ---- ST_GCNN block dispatch ------------------------------------------------------------------
+template <class Cfg>
+int configure_block() {
+  CUDA_TRY(cudaFuncSetAttribute(stgcn_block_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                int(Cfg::SMEM_BYTES)));
+  return MCD_OK;
+}
+
+template <class Cfg>
+int launch_block(const mcd_model* m, int slot, const BlockWeights& w, const BlockIO& io, cudaStream_t s) {
+  static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "block kernel exceeds the 227 KB shared memory of an sm_100 CTA");
+  if (io.n <= 0) return MCD_OK;
+  const int64_t ntiles = (io.n + Cfg::NW - 1) / Cfg::NW;
+  const int grid = int(ntiles < m->num_sms ? ntiles : m->num_sms);
+  {
+    LaunchScope ls(m, slot, io.n, s);
+    stgcn_block_kernel<Cfg><<<grid, kThreads, Cfg::SMEM_BYTES, s>>>(w, io);
+  }
+  return check_launch(kSlotNames[slot]);
+}
+
+// action: 0 = configure (set smem attribute), 1 = launch
+template <int T, int V, int CIN, int COUT, bool EMB, int INMODE, int OUTMODE>
+int block_op(int action, const mcd_model* m, int slot, const BlockWeights* w, const BlockIO* io, cudaStream_t s) {
+  using Cfg = BlockCfg<T, V, CIN, COUT, nw_for(T, 17), EMB, INMODE, OUTMODE>;
+  if (action == 0) return configure_block<Cfg>();
+  return launch_block<Cfg>(m, slot, *w, *io, s);
+}
+
+template <int T>
+int unet_block_op(int action, int idx, const mcd_model* m, const BlockWeights* w, const BlockIO* io, cudaStream_t s) {
+  const int slot = SLOT_UNET0 + idx;
+  switch (idx) {
+    case 0: return block_op<T, 17, 2, 16, true, IN_CF, OUT_CL>(action, m, slot, w, io, s);
+    case 1: return block_op<T, 17, 16, 32, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
+    case 2: return block_op<T, 17, 32, 32, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
+    case 3: return block_op<T, 12, 32, 64, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
+    case 4: return block_op<T, 12, 64, 64, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
+    case 5: return block_op<T, 10, 64, 128, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
+    case 6: return block_op<T, 10, 128, 64, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
+    case 7: return block_op<T, 12, 64, 64, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
+    case 8: return block_op<T, 12, 64, 32, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
+    case 9: return block_op<T, 17, 32, 32, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
+    case 10: return block_op<T, 17, 32, 2, true, IN_CL, OUT_EPS>(action, m, slot, w, io, s);
+  }
+  return fail(MCD_ERR_INVALID_ARG, "bad U-Net block index %d", idx);
+}
+
+template <int TC>
+int enc_block_op(int action, int idx, const mcd_model* m, const BlockWeights* w, const BlockIO* io, cudaStream_t s) {
+  const int slot = SLOT_ENC0 + idx;
+  switch (idx) {
+    case 0: return block_op<TC, 17, 2, 32, false, IN_CF, OUT_CL>(action, m, slot, w, io, s);
+    case 1: return block_op<TC, 17, 32, 16, false, IN_CL, OUT_CL>(action, m, slot, w, io, s);
+    case 2: return block_op<TC, 17, 16, 32, false, IN_CL, OUT_CL>(action, m, slot, w, io, s);
+    case 3: return block_op<TC, 17, 32, 32, false, IN_CL, OUT_CL>(action, m, slot, w, io, s);
+  }
+  return fail(MCD_ERR_INVALID_ARG, "bad encoder block index %d", idx);
+}
+
+// The frame counts this build carries kernels for.  Extend here (and only here).
+#define MCD_FOR_EACH_T(X) X(3) X(24)
+#define MCD_FOR_EACH_TC(X) X(3)
+
+int unet_block_dispatch(int action, int T, int idx, const mcd_model* m, const BlockWeights* w, const BlockIO* io,
+                        cudaStream_t s) {
+  switch (T) {
+#define X(t_) case t_: return unet_block_op<t_>(action, idx, m, w, io, s);
+    MCD_FOR_EACH_T(X)
+#undef X
+  }
+  return fail(MCD_ERR_UNSUPPORTED, "no denoiser kernels compiled for T=%d frames", T);
+}
+int enc_block_dispatch(int action, int Tc, int idx, const mcd_model* m, const BlockWeights* w, const BlockIO* io,
+                       cudaStream_t s) {
+  switch (Tc) {
+#define X(t_) case t_: return enc_block_op<t_>(action, idx, m, w, io, s);
+    MCD_FOR_EACH_TC(X)
+#undef X
+  }
+  return fail(MCD_ERR_UNSUPPORTED, "no conditioning-encoder kernels compiled for T_cond=%d frames", Tc);
+}
+bool t_supported(int T) {
+  switch (T) {
+#define X(t_) case t_: return true;
+    MCD_FOR_EACH_T(X)
+#undef X
+  }
+  return false;
+}
+bool tc_supported(int Tc) {
+  if (Tc == 0) return true;
+  switch (Tc) {
+#define X(t_) case t_: return true;
+    MCD_FOR_EACH_TC(X)
+#undef X
+  }
+  return false;
+}
+
+int launch_resample(const mcd_model* m, int idx, const float* in, const float* skip, float* out, int64_t n, int C,
+                    cudaStream_t s) {
+  const PackedResample& r = m->rs[idx];
+  const int64_t frames = n * m->T;
+  const int grid = grid_for(frames * (C / 4), kThreads, m->num_sms, 8);
+  {
+    LaunchScope ls(m, SLOT_RS0 + idx, n, s);
+    if (r.vin == 17 && r.vout == 12) joint_resample_kernel<17, 12><<<grid, kThreads, 0, s>>>(in, skip, out, r.W, r.b, frames, C);
+    else if (r.vin == 12 && r.vout == 10) joint_resample_kernel<12, 10><<<grid, kThreads, 0, s>>>(in, skip, out, r.W, r.b, frames, C);
+    else if (r.vin == 10 && r.vout == 12) joint_resample_kernel<10, 12><<<grid, kThreads, 0, s>>>(in, skip, out, r.W, r.b, frames, C);
+    else if (r.vin == 12 && r.vout == 17) joint_resample_kernel<12, 17><<<grid, kThreads, 0, s>>>(in, skip, out, r.W, r.b, frames, C);
+    else return fail(MCD_ERR_UNSUPPORTED, "joint resample %d->%d", r.vin, r.vout);
+  }
+  return check_launch(kResample[idx].name);
+}
+
+// ---- workspace -------------------------------------------------------------------------------
+struct Workspace {
+  float *bufA, *bufB, *d1, *d2, *x, *eps;
+};
+size_t align_floats(size_t f) { return (f + 63) / 64 * 64; }  // 256-byte granules
+
+size_t per_window_floats(const mcd_model* m) { return 2 * m->ws_buf + m->ws_d1 + m->ws_d2 + 2 * m->ws_x; }
+
+Workspace carve(const mcd_model* m, float* base, int64_t n) {
+  Workspace w;
+  size_t o = 0;
+  w.bufA = base + o; o += align_floats(m->ws_buf * n);
+  w.bufB = base + o; o += align_floats(m->ws_buf * n);
+  w.d1 = base + o; o += align_floats(m->ws_d1 * n);
+  w.d2 = base + o; o += align_floats(m->ws_d2 * n);
+  w.x = base + o; o += align_floats(m->ws_x * n);
+  w.eps = base + o;
+  return w;
+}
+size_t carve_bytes(const mcd_model* m, int64_t n) {
+  return sizeof(float) * (2 * align_floats(m->ws_buf * n) + align_floats(m->ws_d1 * n) + align_floats(m->ws_d2 * n) +
+                          2 * align_floats(m->ws_x * n));
+}
+
+// ---- the denoiser ----------------------------------------------------------------------------
+int unet_forward_impl(const mcd_model* m, const float* d_x, int64_t n, int t, const float* d_cond, int64_t condB,
+                      int64_t w0, float* d_eps, const Workspace& ws, cudaStream_t s, const char* tap, float* tap_out) {
+  if (t < 0 || t >= m->N) return fail(MCD_ERR_INVALID_ARG, "step t=%d outside [0,%d)", t, m->N);
+  const int T = m->T;
+  BlockIO io{};
+  io.n = n;
+  io.pos = m->d_pos + size_t(t) * m->E;
+  io.cond = d_cond;
+  io.condB = condB > 0 ? condB : 1;
+  io.w0 = w0;
+  io.E = m->E;
+
+  auto tap_copy = [&](const char* name, const float* cl, int C, int V) -> int {
+    if (tap == nullptr || strcmp(tap, name) != 0) return MCD_OK;
+    const int P = T * V;
+    {
+      LaunchScope ls(m, SLOT_TAP, n, s);
+      cl_to_cf_kernel<<<grid_for(n * P * C, kThreads, m->num_sms, 8), kThreads, 0, s>>>(cl, tap_out, n, P, C);
+    }
+    return check_launch("tap");
+  };
+  auto block = [&](int idx, const float* in, float* out) -> int {
+    io.in = in;
+    io.out = out;
+    io.in_sn = 0; io.in_sc = 0; io.in_t0 = 0; io.xres = nullptr;
+    if (idx == 0) { io.in_sn = int64_t(2) * T * 17; io.in_sc = T * 17; }
+    if (idx == kNumUnetBlocks - 1) {
+      io.xres = (tap != nullptr && strcmp(tap, kUnetBlocks[idx].name) == 0) ? nullptr : d_x;
+      if (io.xres == nullptr) io.out = tap_out;  // the layer's own output, reference layout
+    }
+    MCD_TRY(unet_block_dispatch(1, T, idx, m, &m->unet[idx].w, &io, s));
+    if (idx != kNumUnetBlocks - 1) MCD_TRY(tap_copy(kUnetBlocks[idx].name, out, kUnetBlocks[idx].cout, kPyramid[kUnetBlocks[idx].level]));
+    return MCD_OK;
+  };
+  auto resample = [&](int idx, const float* in, const float* skip, float* out, int C) -> int {
+    if (tap != nullptr && strcmp(tap, kResample[idx].name) == 0) {  // hook sees the CNN_layer output before the skip add
+      MCD_TRY(launch_resample(m, idx, in, nullptr, out, n, C, s));
+      return tap_copy(kResample[idx].name, out, C, kPyramid[kResample[idx].lout]);
+    }
+    return launch_resample(m, idx, in, skip, out, n, C, s);
+  };
+
+  // models/stsae/stsae_unet.py:182-219 (_downscale), :365-403 (_upscale)
+  MCD_TRY(block(0, d_x, ws.bufA));
+  MCD_TRY(block(1, ws.bufA, ws.bufB));
+  MCD_TRY(block(2, ws.bufB, ws.d1));
+  MCD_TRY(resample(0, ws.d1, nullptr, ws.bufA, 32));
+  MCD_TRY(block(3, ws.bufA, ws.bufB));
+  MCD_TRY(block(4, ws.bufB, ws.d2));
+  MCD_TRY(resample(1, ws.d2, nullptr, ws.bufA, 64));
+  MCD_TRY(block(5, ws.bufA, ws.bufB));
+  MCD_TRY(block(6, ws.bufB, ws.bufA));
+  MCD_TRY(resample(2, ws.bufA, ws.d2, ws.bufB, 64));
+  MCD_TRY(block(7, ws.bufB, ws.bufA));
+  MCD_TRY(block(8, ws.bufA, ws.bufB));
+  MCD_TRY(resample(3, ws.bufB, ws.d1, ws.bufA, 32));
+  MCD_TRY(block(9, ws.bufA, ws.bufB));
+  MCD_TRY(block(10, ws.bufB, d_eps));
+  return MCD_OK;
+}
+
+int cond_encode_impl(const mcd_model* m, const float* d_data, int64_t B, float* d_emb, const Workspace& ws,
+                     cudaStream_t s) {
+  const int Tc = m->Tc, V = 17;
+  BlockIO io{};
+  io.n = B;
+  io.condB = 1;
+  io.E = m->E;
+  const float* in = d_data;
+  float* bufs[2] = {ws.bufA, ws.bufB};
+  for (int i = 0; i < kNumEncBlocks; ++i) {
+    io.in = in;
+    io.out = bufs[i & 1];
+    io.in_sn = 0; io.in_sc = 0; io.in_t0 = 0;
+    if (i == 0) { io.in_sn = int64_t(2) * m->cfg.n_frames * V; io.in_sc = m->cfg.n_frames * V; io.in_t0 = m->t0_cond; }
+    MCD_TRY(enc_block_dispatch(1, Tc, i, m, &m->enc[i].w, &io, s));
+    in = io.out;
+  }
+  const int K = m->enc[kNumEncBlocks - 1].cout * Tc * V;
+  {
+    LaunchScope ls(m, SLOT_BTLNK, B, s);
+    bottleneck_kernel<<<grid_for(B * 32, kThreads, 1 << 20, 1), kThreads, 0, s>>>(in, m->d_btl_W, m->d_btl_b, d_emb, B, K,
+                                                                                    m->E);
+  }
+  return check_launch("bottleneck");
+}
+
+DdpmArgs make_ddpm_args(const mcd_model* m, int t, const float* noise, int64_t noise_B, int slot, int64_t virt0,
+                        uint64_t seed, int64_t first_window) {
+  DdpmArgs a{};
+  if (t >= 1) mcd_ddpm_coefficients(m->N, t, &a.c1, &a.c2, &a.c3);
+  a.add_noise = t > 1;
+  a.noise = noise;
+  a.noise_B = noise_B > 0 ? noise_B : 1;
+  a.noise_slots = m->N - 1 > 1 ? m->N - 1 : 1;
+  a.slot = slot;
+  a.virt0 = virt0;
+  a.seed = seed;
+  a.first_window = first_window;
+  return a;
+}
+
+int launch_ddpm(const mcd_model* m, float* x, const float* eps, int64_t n, const DdpmArgs& a, cudaStream_t s) {
+  const int per = 2 * m->T * 17;
+  {
+    LaunchScope ls(m, SLOT_DDPM, n, s);
+    ddpm_step_kernel<<<grid_for(n * per, kThreads * 4, m->num_sms, 16), kThreads, 0, s>>>(x, eps, n, per, a);
+  }
+  return check_launch("ddpm_step");
+}
+int launch_randn(const mcd_model* m, float* x, int64_t n, const DdpmArgs& a, cudaStream_t s) {
+  const int per = 2 * m->T * 17;
+  {
+    LaunchScope ls(m, SLOT_RANDN, n, s);
+    randn_kernel<<<grid_for(n * per, kThreads * 4, m->num_sms, 16), kThreads, 0, s>>>(x, n, per, a);
+  }
+  return check_launch("randn");
+}
+int launch_loss(const mcd_model* m, const float* x0, const float* data, float* losses, int64_t nv, int64_t virt0,
+                int64_t B, cudaStream_t s) {
+  {
+    LaunchScope ls(m, SLOT_LOSS, nv, s);
+    window_loss_kernel<<<grid_for(nv * 32, kThreads, 1 << 20, 1), kThreads, 0, s>>>(
+        x0, data, losses, nv, virt0, B, m->T * 17, 17, m->cfg.n_frames, m->t0_corrupt, m->cfg.loss_fn);
+  }
+  return check_launch("window_loss");
+}
+int launch_best(const mcd_model* m, const float* losses, float* best, float* worst, int64_t B, int G, cudaStream_t s) {
+  {
+    LaunchScope ls(m, SLOT_BEST, B, s);
+    best_worst_kernel<<<grid_for(B, kThreads, 1 << 20, 1), kThreads, 0, s>>>(losses, best, worst, B, G);
+  }
+  return check_launch("best_worst");
+}
+
+// ---- weight packing --------------------------------------------------------------------------
+struct Arena {
+  std::vector<float> h;
+  size_t alloc(size_t n) {
+    size_t o = h.size();
+    h.resize(o + align_floats(n), 0.0f);
+    return o;
+  }
+};
+
+const std::vector<float>* find(const mcd_model* m, const std::string& name, size_t numel, std::string* missing) {
+  auto it = m->tensors.find(name);
+  if (it == m->tensors.end()) {
+    if (missing->empty()) *missing = name;
+    return nullptr;
+  }
+  if (it->second.size() != numel) {
+    if (missing->empty()) {
+      char buf[256];
+      snprintf(buf, sizeof(buf), "%s (has %zu elements, expected %zu)", name.c_str(), it->second.size(), numel);
+      *missing = buf;
+    }
+    return nullptr;
+  }
+  return &it->second;
+}
+
+// scale/shift of an eval-mode BatchNorm2d (eps = 1e-5, models/gcae/stsgcn.py:65):  y = x*s + h
+bool bn_fold(const mcd_model* m, const std::string& p, int C, std::vector<double>* s, std::vector<double>* h,
+             std::string* missing) {
+  auto* g = find(m, p + "weight", C, missing);
+  auto* b = find(m, p + "bias", C, missing);
+  auto* mu = find(m, p + "running_mean", C, missing);
+  auto* var = find(m, p + "running_var", C, missing);
+  if (!g || !b || !mu || !var) return false;
+  s->resize(C);
+  h->resize(C);
+  for (int c = 0; c < C; ++c) {
+    (*s)[c] = double((*g)[c]) / std::sqrt(double((*var)[c]) + 1e-5);
+    (*h)[c] = double((*b)[c]) - double((*mu)[c]) * (*s)[c];
+  }
+  return true;
+}
+
+struct BlockOffsets { size_t A, Tm, W, Wr, bias, WE, bE; };
+
+bool pack_block(const mcd_model* m, Arena* ar, const std::string& p, int cin, int cout, int T, int V, bool emb, int E,
+                PackedBlock* pb, BlockOffsets* off, std::string* missing) {
+  const int VP = (V + 3) / 4 * 4, TP4 = (T + 3) / 4 * 4, TMS = T * TP4 + 4;
+  const int cinp = cin < 4 ? 4 : cin;
+  pb->cin = cin; pb->cout = cout; pb->V = V; pb->T = T; pb->emb = emb; pb->resconv = cin != cout;
+  auto* A = find(m, p + "gcn.A", size_t(T) * V * V, missing);
+  auto* Tm = find(m, p + "gcn.T", size_t(V) * T * T, missing);
+  auto* W = find(m, p + "tcn.0.weight", size_t(cout) * cin, missing);
+  auto* b = find(m, p + "tcn.0.bias", cout, missing);
+  auto* pr = find(m, p + "prelu.weight", 1, missing);
+  std::vector<double> s, h, sr, hr;
+  bool ok = bn_fold(m, p + "tcn.1.", cout, &s, &h, missing);
+  const std::vector<float>*Wr = nullptr, *br = nullptr, *WE = nullptr, *bE = nullptr;
+  if (pb->resconv) {
+    Wr = find(m, p + "residual.0.weight", size_t(cout) * cin, missing);
+    br = find(m, p + "residual.0.bias", cout, missing);
+    ok = bn_fold(m, p + "residual.1.", cout, &sr, &hr, missing) && ok && Wr && br;
+  }
+  if (emb) {
+    WE = find(m, p + "emb_layer.1.weight", size_t(cout) * E, missing);
+    bE = find(m, p + "emb_layer.1.bias", cout, missing);
+    ok = ok && WE && bE;
+  }
+  if (!ok || !A || !Tm || !W || !b || !pr) return false;
+
+  off->A = ar->alloc(size_t(T) * V * VP);
+  for (int t = 0; t < T; ++t)
+    for (int v = 0; v < V; ++v)
+      for (int w = 0; w < V; ++w) ar->h[off->A + (size_t(t) * V + v) * VP + w] = (*A)[(size_t(t) * V + v) * V + w];
+  off->Tm = ar->alloc(size_t(V) * TMS);
+  for (int v = 0; v < V; ++v)
+    for (int t = 0; t < T; ++t)
+      for (int q = 0; q < T; ++q) ar->h[off->Tm + size_t(v) * TMS + t * TP4 + q] = (*Tm)[(size_t(v) * T + t) * T + q];
+  off->W = ar->alloc(size_t(cinp) * cout);
+  for (int k = 0; k < cin; ++k)
+    for (int co = 0; co < cout; ++co) ar->h[off->W + size_t(k) * cout + co] = float(double((*W)[size_t(co) * cin + k]) * s[co]);
+  off->bias = ar->alloc(cout);
+  for (int co = 0; co < cout; ++co) ar->h[off->bias + co] = float(double((*b)[co]) * s[co] + h[co]);
+  off->Wr = 0;
+  if (pb->resconv) {
+    off->Wr = ar->alloc(size_t(cinp) * cout);
+    for (int k = 0; k < cin; ++k)
+      for (int co = 0; co < cout; ++co)
+        ar->h[off->Wr + size_t(k) * cout + co] = float(double((*Wr)[size_t(co) * cin + k]) * sr[co]);
+    for (int co = 0; co < cout; ++co)
+      ar->h[off->bias + co] = float(double((*b)[co]) * s[co] + h[co] + double((*br)[co]) * sr[co] + hr[co]);
+  }
+  off->WE = off->bE = 0;
+  if (emb) {
+    off->WE = ar->alloc(size_t(E) * cout);
+    for (int j = 0; j < E; ++j)
+      for (int co = 0; co < cout; ++co) ar->h[off->WE + size_t(j) * cout + co] = (*WE)[size_t(co) * E + j];
+    off->bE = ar->alloc(cout);
+    for (int co = 0; co < cout; ++co) ar->h[off->bE + co] = (*bE)[co];
+  }
+  pb->w.prelu = (*pr)[0];
+  return true;
+}
+
+void bind_block(PackedBlock* pb, const BlockOffsets& off, const float* base) {
+  pb->w.A = base + off.A;
+  pb->w.Tm = base + off.Tm;
+  pb->w.Wt = base + off.W;
+  pb->w.Wrt = pb->resconv ? base + off.Wr : nullptr;
+  pb->w.bias = base + off.bias;
+  pb->w.WEt = pb->emb ? base + off.WE : nullptr;
+  pb->w.bE = pb->emb ? base + off.bE : nullptr;
+}
+
+void free_device(mcd_model* m) {
+  if (m->d_arena) cudaFree(m->d_arena);
+  m->d_arena = nullptr;
+}
+
+int check_ready(const mcd_model* m) {
+  if (m == nullptr) return fail(MCD_ERR_INVALID_ARG, "model handle is NULL");
+  if (!m->finalized) return fail(MCD_ERR_NOT_FINALIZED, "mcd_model_finalize has not been called on this handle");
+  return MCD_OK;
+}
+
+int64_t tile_unit(const mcd_model* m) { return int64_t(m->num_sms) * nw_for(m->T, 17); }
+
+// fp32 FMA probe: 8 independent chains per thread, 4096 FMAs each
+__global__ void __launch_bounds__(256) fma_probe_kernel(float* out, int iters) {
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = float(threadIdx.x + i) * 1e-3f;
+  const float b = 1.0000001f, c = 1e-7f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fmaf(a[i], b, c);
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += a[i];
+  if (sum == 12345.678f) out[0] = sum;  // keep the chains alive
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int mcd_abi_version(void) { return MCD_ABI_VERSION; }
+const char* mcd_last_error(void) { return g_err.c_str(); }
+int mcd_shape_supported(int32_t T, int32_t T_cond) { return (t_supported(T) && tc_supported(T_cond)) ? 1 : 0; }
+
+// utils/diffusion_utils.py:8-14 (betas_for_alpha_bar, float64) -> :38-44 (fp32 tensor);
+// models/mocodad.py:803-808 (alpha = 1 - beta, alpha_hat = cumprod(alpha), both fp32).
+int mcd_schedule(int32_t noise_steps, float* h_beta, float* h_alpha, float* h_alpha_hat) {
+  if (noise_steps < 1) return fail(MCD_ERR_INVALID_ARG, "noise_steps must be >= 1 (got %d)", noise_steps);
+  const double pi = 3.141592653589793;
+  auto alpha_bar = [&](double t) {
+    double c = std::cos((t + 0.008) / 1.008 * pi / 2);
+    return c * c;
+  };
+  // torch.cumprod on CPU accumulates float32 inputs in double (at::acc_type<float, false>) and rounds
+  // each prefix to float; the reference builds the schedule on the CPU (mocodad.py:799-808).
+  double cum = 1.0;
+  for (int i = 0; i < noise_steps; ++i) {
+    double t1 = double(i) / noise_steps, t2 = double(i + 1) / noise_steps;
+    double b = 1 - alpha_bar(t2) / alpha_bar(t1);
+    if (b > 0.999) b = 0.999;
+    const float bf = float(b);
+    volatile float af = 1.0f - bf;
+    cum = cum * double(af);
+    if (h_beta) h_beta[i] = bf;
+    if (h_alpha) h_alpha[i] = af;
+    if (h_alpha_hat) h_alpha_hat[i] = float(cum);
+  }
+  return MCD_OK;
+}
+
+// models/stsae/stsae_unet.py:161-179
+int mcd_pos_encoding(int32_t t, int32_t channels, float* h_out) {
+  if (channels < 2 || (channels & 1) || h_out == nullptr) return fail(MCD_ERR_INVALID_ARG, "pos_encoding: channels=%d", channels);
+  const int half = channels / 2;
+  for (int k = 0; k < half; ++k) {
+    const float ex = float(2 * k) / float(channels);
+    const float inv_freq = 1.0f / powf(10000.0f, ex);
+    const float arg = float(t) * inv_freq;
+    h_out[k] = sinf(arg);
+    h_out[half + k] = cosf(arg);
+  }
+  return MCD_OK;
+}
+
+// models/mocodad.py:172-178, evaluated in fp32 exactly as the eager expression does
+int mcd_ddpm_coefficients(int32_t noise_steps, int32_t t, float* c1, float* c2, float* c3) {
+  if (t < 0 || t >= noise_steps) return fail(MCD_ERR_INVALID_ARG, "ddpm step t=%d outside [0,%d)", t, noise_steps);
+  std::vector<float> b(noise_steps), a(noise_steps), ah(noise_steps);
+  MCD_TRY(mcd_schedule(noise_steps, b.data(), a.data(), ah.data()));
+  volatile float sa = sqrtf(a[t]);
+  volatile float one_m_a = 1.0f - a[t];
+  volatile float one_m_ah = 1.0f - ah[t];
+  volatile float s1 = sqrtf(one_m_ah);
+  if (c1) *c1 = 1.0f / sa;
+  if (c2) *c2 = one_m_a / s1;
+  if (c3) *c3 = sqrtf(b[t]);
+  return MCD_OK;
+}
+
+int mcd_model_create(const mcd_config* cfg, mcd_model** out) {
+  if (cfg == nullptr || out == nullptr) return fail(MCD_ERR_INVALID_ARG, "mcd_model_create: NULL argument");
+  *out = nullptr;
+  if (cfg->n_coords != 2) return fail(MCD_ERR_UNSUPPORTED, "num_coords=%d (kernels are built for 2)", cfg->n_coords);
+  if (cfg->n_joints != 17)
+    return fail(MCD_ERR_UNSUPPORTED, "n_joints=%d: the denoiser's joint pyramid is fixed at 17/12/10 (stsae_unet.py:11)", cfg->n_joints);
+  if (cfg->n_frames_cond < 0 || cfg->n_frames_cond >= cfg->n_frames)
+    return fail(MCD_ERR_INVALID_ARG, "n_frames_cond=%d with n_frames=%d", cfg->n_frames_cond, cfg->n_frames);
+  const int T = cfg->n_frames - cfg->n_frames_cond;
+  if (!t_supported(T)) return fail(MCD_ERR_UNSUPPORTED, "no denoiser kernels compiled for T=%d frames", T);
+  if (!tc_supported(cfg->n_frames_cond))
+    return fail(MCD_ERR_UNSUPPORTED, "no conditioning-encoder kernels compiled for T_cond=%d frames", cfg->n_frames_cond);
+  if (cfg->embedding_dim < 2 || cfg->embedding_dim > kMaxE || (cfg->embedding_dim & 1))
+    return fail(MCD_ERR_UNSUPPORTED, "embedding_dim=%d (supported: even, 2..%d)", cfg->embedding_dim, kMaxE);
+  if (cfg->n_frames_cond > 0 &&
+      (cfg->cond_channels[0] != 32 || cfg->cond_channels[1] != 16 || cfg->cond_channels[2] != 32 || cfg->cond_h_dim != 32))
+    return fail(MCD_ERR_UNSUPPORTED, "conditioning encoder channels [%d,%d,%d]+h_dim %d (kernels are built for [32,16,32]+32)",
+                cfg->cond_channels[0], cfg->cond_channels[1], cfg->cond_channels[2], cfg->cond_h_dim);
+  if (cfg->noise_steps < 1 || cfg->noise_steps > 65535) return fail(MCD_ERR_INVALID_ARG, "noise_steps=%d", cfg->noise_steps);
+  if (cfg->loss_fn < 0 || cfg->loss_fn > 2) return fail(MCD_ERR_INVALID_ARG, "loss_fn=%d", cfg->loss_fn);
+  if (2 * T * 17 > 65535) return fail(MCD_ERR_UNSUPPORTED, "window too large for the Philox element counter");
+  mcd_model* m = new mcd_model();
+  m->cfg = *cfg;
+  m->T = T;
+  m->Tc = cfg->n_frames_cond;
+  m->t0_cond = cfg->cond_first ? 0 : T;
+  m->t0_corrupt = (cfg->n_frames_cond > 0 && cfg->cond_first) ? cfg->n_frames_cond : 0;
+  m->E = cfg->embedding_dim;
+  m->N = cfg->noise_steps;
+  m->beta.resize(m->N); m->alpha.resize(m->N); m->alpha_hat.resize(m->N);
+  mcd_schedule(m->N, m->beta.data(), m->alpha.data(), m->alpha_hat.data());
+  size_t buf = size_t(T) * 1280;  // max over levels of C*T*V: 32*17, 64*12, 128*10
+  if (size_t(m->Tc) * 17 * 32 > buf) buf = size_t(m->Tc) * 17 * 32;
+  m->ws_buf = buf;
+  m->ws_d1 = size_t(32) * T * 17;
+  m->ws_d2 = size_t(64) * T * 12;
+  m->ws_x = size_t(2) * T * 17;
+  *out = m;
+  return MCD_OK;
+}
+
+int mcd_model_set_tensor(mcd_model* m, const char* name, const float* h_data, int64_t numel) {
+  if (m == nullptr || name == nullptr || (h_data == nullptr && numel > 0) || numel < 0)
+    return fail(MCD_ERR_INVALID_ARG, "mcd_model_set_tensor: bad argument");
+  m->tensors[name].assign(h_data, h_data + numel);
+  m->finalized = false;
+  return MCD_OK;
+}
+
+int mcd_model_finalize(mcd_model* m) {
+  if (m == nullptr) return fail(MCD_ERR_INVALID_ARG, "model handle is NULL");
+  Arena ar;
+  std::string missing;
+  BlockOffsets uo[kNumUnetBlocks], eo[kNumEncBlocks];
+  bool ok = true;
+  for (int i = 0; i < kNumUnetBlocks; ++i) {
+    const BlockShape& b = kUnetBlocks[i];
+    ok = pack_block(m, &ar, std::string("model.") + b.name + ".", b.cin, b.cout, m->T, kPyramid[b.level], true, m->E, &m->unet[i],
+                    &uo[i], &missing) && ok;
+  }
+  size_t rsW[kNumResample] = {}, rsb[kNumResample] = {};
+  for (int i = 0; i < kNumResample; ++i) {
+    const int vin = kPyramid[kResample[i].lin], vout = kPyramid[kResample[i].lout];
+    const std::string p = std::string("model.") + kResample[i].name + ".block.";
+    auto* W = find(m, p + "0.weight", size_t(vout) * vin, &missing);
+    auto* b = find(m, p + "0.bias", vout, &missing);
+    std::vector<double> s, h;
+    if (!bn_fold(m, p + "1.", vout, &s, &h, &missing) || !W || !b) { ok = false; continue; }
+    rsW[i] = ar.alloc(size_t(vout) * vin);
+    rsb[i] = ar.alloc(vout);
+    for (int w = 0; w < vout; ++w) {
+      for (int v = 0; v < vin; ++v) ar.h[rsW[i] + size_t(w) * vin + v] = float(double((*W)[size_t(w) * vin + v]) * s[w]);
+      ar.h[rsb[i] + w] = float(double((*b)[w]) * s[w] + h[w]);
+    }
+    m->rs[i].vin = vin;
+    m->rs[i].vout = vout;
+  }
+  size_t btlW = 0, btlb = 0;
+  if (m->Tc > 0) {
+    const int chans[kNumEncBlocks + 1] = {2, m->cfg.cond_channels[0], m->cfg.cond_channels[1], m->cfg.cond_channels[2], m->cfg.cond_h_dim};
+    for (int i = 0; i < kNumEncBlocks; ++i) {
+      char p[128];
+      snprintf(p, sizeof(p), "condition_encoder.encoder.model_layers.%d.", i);
+      ok = pack_block(m, &ar, p, chans[i], chans[i + 1], m->Tc, 17, false, m->E, &m->enc[i], &eo[i], &missing) && ok;
+    }
+    // models/stsae/stsae.py:87 flattens [C,T,V] row-major; our activations are [P][C]
+    const int C = m->cfg.cond_h_dim, P = m->Tc * 17, K = C * P, L = m->E;
+    auto* W = find(m, "condition_encoder.btlnk.weight", size_t(L) * K, &missing);
+    auto* b = find(m, "condition_encoder.btlnk.bias", L, &missing);
+    if (W && b) {
+      btlW = ar.alloc(size_t(K) * L);
+      btlb = ar.alloc(L);
+      for (int c = 0; c < C; ++c)
+        for (int p = 0; p < P; ++p)
+          for (int l = 0; l < L; ++l) ar.h[btlW + (size_t(p) * C + c) * L + l] = (*W)[size_t(l) * K + size_t(c) * P + p];
+      for (int l = 0; l < L; ++l) ar.h[btlb + l] = (*b)[l];
+    } else {
+      ok = false;
+    }
+  }
+  if (!ok) return fail(MCD_ERR_MISSING_TENSOR, "state_dict entry missing or mis-sized: %s", missing.c_str());
+  const size_t pos_off = ar.alloc(size_t(m->N) * m->E);
+  for (int t = 0; t < m->N; ++t) mcd_pos_encoding(t, m->E, &ar.h[pos_off + size_t(t) * m->E]);
+
+  CUDA_TRY(cudaSetDevice(m->cfg.device));
+  int sms = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->cfg.device));
+  m->num_sms = sms;
+  free_device(m);
+  CUDA_TRY(cudaMalloc(&m->d_arena, ar.h.size() * sizeof(float)));
+  m->arena_floats = ar.h.size();
+  CUDA_TRY(cudaMemcpy(m->d_arena, ar.h.data(), ar.h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  for (int i = 0; i < kNumUnetBlocks; ++i) bind_block(&m->unet[i], uo[i], m->d_arena);
+  for (int i = 0; i < kNumResample; ++i) { m->rs[i].W = m->d_arena + rsW[i]; m->rs[i].b = m->d_arena + rsb[i]; }
+  if (m->Tc > 0) {
+    for (int i = 0; i < kNumEncBlocks; ++i) bind_block(&m->enc[i], eo[i], m->d_arena);
+    m->d_btl_W = m->d_arena + btlW;
+    m->d_btl_b = m->d_arena + btlb;
+  }
+  m->d_pos = m->d_arena + pos_off;
+  for (int i = 0; i < kNumUnetBlocks; ++i) MCD_TRY(unet_block_dispatch(0, m->T, i, m, nullptr, nullptr, nullptr));
+  if (m->Tc > 0)
+    for (int i = 0; i < kNumEncBlocks; ++i) MCD_TRY(enc_block_dispatch(0, m->Tc, i, m, nullptr, nullptr, nullptr));
+  m->finalized = true;
+  return MCD_OK;
+}
+
+void mcd_model_destroy(mcd_model* m) {
+  if (m == nullptr) return;
+  if (m->d_arena || m->d_host_ws || m->own_stream || !m->prof_events.empty()) cudaSetDevice(m->cfg.device);
+  free_device(m);
+  if (m->d_host_data) cudaFree(m->d_host_data);
+  if (m->d_host_best) cudaFree(m->d_host_best);
+  if (m->d_host_ws) cudaFree(m->d_host_ws);
+  if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  for (auto& e : m->prof_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  delete m;
+}
+
+size_t mcd_workspace_bytes(const mcd_model* m, int64_t n_virtual) {
+  if (m == nullptr || n_virtual < 1) return 0;
+  return carve_bytes(m, n_virtual) + size_t(n_virtual) * (m->E + 1) * sizeof(float) + 1024;
+}
+
+int mcd_cond_encode(const mcd_model* m, const float* d_data, int64_t B, float* d_cond_emb, void* d_ws, size_t ws_bytes,
+                    void* stream) {
+  MCD_TRY(check_ready(m));
+  if (m->Tc == 0) return fail(MCD_ERR_UNSUPPORTED, "model was created with n_frames_cond = 0 ('no_condition')");
+  if (d_data == nullptr || d_cond_emb == nullptr || d_ws == nullptr || B < 0) return fail(MCD_ERR_INVALID_ARG, "mcd_cond_encode: bad argument");
+  if (B == 0) return MCD_OK;
+  if (ws_bytes < carve_bytes(m, B)) return fail(MCD_ERR_WORKSPACE, "workspace %zu B < %zu B needed for %lld windows", ws_bytes, carve_bytes(m, B), (long long)B);
+  return cond_encode_impl(m, d_data, B, d_cond_emb, carve(m, static_cast<float*>(d_ws), B), static_cast<cudaStream_t>(stream));
+}
+
+int mcd_unet_forward(const mcd_model* m, const float* d_x, int64_t n, int32_t t, const float* d_cond_emb, int64_t cond_B,
+                     float* d_eps, void* d_ws, size_t ws_bytes, void* stream) {
+  MCD_TRY(check_ready(m));
+  if (d_x == nullptr || d_eps == nullptr || d_ws == nullptr || n < 0) return fail(MCD_ERR_INVALID_ARG, "mcd_unet_forward: bad argument");
+  if (n == 0) return MCD_OK;
+  if (ws_bytes < carve_bytes(m, n)) return fail(MCD_ERR_WORKSPACE, "workspace %zu B < %zu B needed for %lld windows", ws_bytes, carve_bytes(m, n), (long long)n);
+  return unet_forward_impl(m, d_x, n, t, d_cond_emb, cond_B, 0, d_eps, carve(m, static_cast<float*>(d_ws), n),
+                           static_cast<cudaStream_t>(stream), nullptr, nullptr);
+}
+
+int mcd_unet_tap(const mcd_model* m, const float* d_x, int64_t n, int32_t t, const float* d_cond_emb, int64_t cond_B,
+                 const char* layer_name, float* d_out, void* d_ws, size_t ws_bytes, void* stream) {
+  MCD_TRY(check_ready(m));
+  if (d_x == nullptr || d_out == nullptr || d_ws == nullptr || layer_name == nullptr || n < 0)
+    return fail(MCD_ERR_INVALID_ARG, "mcd_unet_tap: bad argument");
+  bool known = false;
+  for (auto& b : kUnetBlocks) known = known || strcmp(b.name, layer_name) == 0;
+  for (auto& r : kResample) known = known || strcmp(r.name, layer_name) == 0;
+  if (!known) return fail(MCD_ERR_INVALID_ARG, "unknown denoiser layer '%s'", layer_name);
+  if (n == 0) return MCD_OK;
+  if (ws_bytes < carve_bytes(m, n)) return fail(MCD_ERR_WORKSPACE, "workspace %zu B < %zu B needed", ws_bytes, carve_bytes(m, n));
+  Workspace ws = carve(m, static_cast<float*>(d_ws), n);
+  return unet_forward_impl(m, d_x, n, t, d_cond_emb, cond_B, 0, ws.eps, ws, static_cast<cudaStream_t>(stream), layer_name, d_out);
+}
+
+int mcd_ddpm_step(const mcd_model* m, float* d_x, const float* d_eps, const float* d_noise, int64_t n, int32_t t,
+                  uint64_t seed, int64_t first_window, int32_t sample, int32_t noise_slot, void* stream) {
+  MCD_TRY(check_ready(m));
+  if (d_x == nullptr || d_eps == nullptr || n < 0) return fail(MCD_ERR_INVALID_ARG, "mcd_ddpm_step: bad argument");
+  if (t < 1 || t >= m->N) return fail(MCD_ERR_INVALID_ARG, "ddpm step t=%d outside [1,%d)", t, m->N);
+  if (n == 0) return MCD_OK;
+  // a plain [n,2,T,V] noise tensor: one sample of n windows, one slot
+  DdpmArgs a = make_ddpm_args(m, t, d_noise, n, d_noise ? 0 : noise_slot, int64_t(sample) * n, seed, first_window);
+  if (d_noise) { a.noise_slots = 1; a.virt0 = 0; }
+  return launch_ddpm(m, d_x, d_eps, n, a, static_cast<cudaStream_t>(stream));
+}
+
+int mcd_randn_windows(const mcd_model* m, float* d_x, int64_t n, uint64_t seed, int64_t first_window, int32_t sample,
+                      int32_t noise_slot, void* stream) {
+  MCD_TRY(check_ready(m));
+  if (d_x == nullptr || n < 0) return fail(MCD_ERR_INVALID_ARG, "mcd_randn_windows: bad argument");
+  if (n == 0) return MCD_OK;
+  DdpmArgs a = make_ddpm_args(m, 0, nullptr, n, noise_slot, int64_t(sample) * n, seed, first_window);
+  return launch_randn(m, d_x, n, a, static_cast<cudaStream_t>(stream));
+}
+
+int mcd_window_loss(const mcd_model* m, const float* d_x0, const float* d_data, int64_t B, int32_t G, float* d_losses,
+                    float* d_best, float* d_worst, void* stream) {
+  MCD_TRY(check_ready(m));
+  if (d_x0 == nullptr || d_data == nullptr || B < 0 || G < 1) return fail(MCD_ERR_INVALID_ARG, "mcd_window_loss: bad argument");
+  if (B == 0) return MCD_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (d_losses == nullptr) {
+    if (G != 1 || (d_best == nullptr && d_worst == nullptr))
+      return fail(MCD_ERR_INVALID_ARG, "mcd_window_loss: d_losses may be NULL only when G == 1 and d_best or d_worst is given");
+    float* dst = d_best ? d_best : d_worst;
+    MCD_TRY(launch_loss(m, d_x0, d_data, dst, B, 0, B, s));
+    if (d_best && d_worst) CUDA_TRY(cudaMemcpyAsync(d_worst, d_best, B * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return MCD_OK;
+  }
+  MCD_TRY(launch_loss(m, d_x0, d_data, d_losses, int64_t(G) * B, 0, B, s));
+  if (d_best || d_worst) MCD_TRY(launch_best(m, d_losses, d_best, d_worst, B, G, s));
+  return MCD_OK;
+}
+
+int mcd_reverse_diffusion(const mcd_model* m, const float* d_data, int64_t B, int32_t G, const float* d_noise, uint64_t seed,
+                          int64_t first_window, float* d_losses, float* d_best, float* d_worst, float* d_x0, void* d_ws,
+                          size_t ws_bytes, void* stream) {
+  MCD_TRY(check_ready(m));
+  if (d_data == nullptr || d_ws == nullptr || B < 0 || G < 1) return fail(MCD_ERR_INVALID_ARG, "mcd_reverse_diffusion: bad argument");
+  if (B == 0) return MCD_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t nv = int64_t(G) * B;
+  const int per = 2 * m->T * 17;
+
+  // fixed part of the workspace: conditioning embedding [B,E] and (when the caller keeps none) losses [G,B]
+  float* base = static_cast<float*>(d_ws);
+  size_t fixed = 0;
+  float* cond_emb = nullptr;
+  if (m->Tc > 0) { cond_emb = base + fixed; fixed += align_floats(size_t(B) * m->E); }
+  float* losses = d_losses;
+  if (losses == nullptr) { losses = base + fixed; fixed += align_floats(size_t(nv)); }
+  if (ws_bytes < fixed * sizeof(float) + carve_bytes(m, 1))
+    return fail(MCD_ERR_WORKSPACE, "workspace %zu B cannot hold one window tile (%zu B fixed + %zu B per window)", ws_bytes,
+                fixed * sizeof(float), carve_bytes(m, 1));
+  float* tile_base = base + fixed;
+  const size_t tile_bytes = ws_bytes - fixed * sizeof(float);
+  // largest n with carve_bytes(n) <= tile_bytes (carve_bytes is monotone; per-buffer rounding costs < 6 granules)
+  int64_t n_tile = int64_t((tile_bytes - 6 * 256) / (per_window_floats(m) * sizeof(float)));
+  while (n_tile > 1 && carve_bytes(m, n_tile) > tile_bytes) --n_tile;
+  if (n_tile < 1) n_tile = 1;
+  if (n_tile > nv) n_tile = nv;
+  const int64_t unit = tile_unit(m);
+  if (n_tile < nv && n_tile > unit) n_tile -= n_tile % unit;  // whole waves of CTA tiles
+
+  // a3: conditioning embedding, once per batch (mocodad.py:157)
+  if (m->Tc > 0) {
+    for (int64_t b0 = 0; b0 < B; b0 += n_tile) {
+      const int64_t nb = (B - b0) < n_tile ? (B - b0) : n_tile;
+      MCD_TRY(cond_encode_impl(m, d_data + b0 * 2 * m->cfg.n_frames * 17, nb, cond_emb + b0 * m->E, carve(m, tile_base, nb), s));
+    }
+  }
+
+  for (int64_t v0 = 0; v0 < nv; v0 += n_tile) {
+    const int64_t n = (nv - v0) < n_tile ? (nv - v0) : n_tile;
+    Workspace ws = carve(m, tile_base, n);
+    float* x = d_x0 ? d_x0 + v0 * per : ws.x;
+    // mocodad.py:162  x_T
+    MCD_TRY(launch_randn(m, x, n, make_ddpm_args(m, 0, d_noise, B, 0, v0, seed, first_window), s));
+    int slot = 0;
+    for (int t = m->N - 1; t >= 1; --t) {  // mocodad.py:163
+      MCD_TRY(unet_forward_impl(m, x, n, t, cond_emb, B, v0, ws.eps, ws, s, nullptr, nullptr));
+      ++slot;
+      MCD_TRY(launch_ddpm(m, x, ws.eps, n, make_ddpm_args(m, t, d_noise, B, slot, v0, seed, first_window), s));
+    }
+    MCD_TRY(launch_loss(m, x, d_data, losses + v0, n, v0, B, s));  // mocodad.py:484
+  }
+  if (d_best || d_worst) MCD_TRY(launch_best(m, losses, d_best, d_worst, B, G, s));  // mocodad.py:504-512
+  return MCD_OK;
+}
+
+int mcd_score_windows_host(mcd_model* m, const float* h_data, int64_t B, int32_t G, uint64_t seed, int64_t first_window,
+                           float* h_best) {
+  MCD_TRY(check_ready(m));
+  if (h_data == nullptr || h_best == nullptr || B < 0 || G < 1) return fail(MCD_ERR_INVALID_ARG, "mcd_score_windows_host: bad argument");
+  if (B == 0) return MCD_OK;
+  CUDA_TRY(cudaSetDevice(m->cfg.device));
+  if (m->own_stream == nullptr) CUDA_TRY(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+  const size_t data_floats = size_t(B) * 2 * m->cfg.n_frames * 17;
+  if (data_floats > m->host_data_floats) {
+    if (m->d_host_data) cudaFree(m->d_host_data);
+    m->d_host_data = nullptr; m->host_data_floats = 0;
+    CUDA_TRY(cudaMalloc(&m->d_host_data, data_floats * sizeof(float)));
+    m->host_data_floats = data_floats;
+  }
+  if (size_t(B) > m->host_best_floats) {
+    if (m->d_host_best) cudaFree(m->d_host_best);
+    m->d_host_best = nullptr; m->host_best_floats = 0;
+    CUDA_TRY(cudaMalloc(&m->d_host_best, size_t(B) * sizeof(float)));
+    m->host_best_floats = size_t(B);
+  }
+  const int64_t nv = int64_t(G) * B;
+  int64_t n_tile = tile_unit(m) * 16;
+  if (n_tile > nv) n_tile = nv;
+  const size_t need = carve_bytes(m, n_tile) + (align_floats(size_t(B) * m->E) + align_floats(size_t(nv))) * sizeof(float);
+  if (need > m->host_ws_bytes) {
+    if (m->d_host_ws) cudaFree(m->d_host_ws);
+    m->d_host_ws = nullptr; m->host_ws_bytes = 0;
+    CUDA_TRY(cudaMalloc(&m->d_host_ws, need));
+    m->host_ws_bytes = need;
+  }
+  cudaStream_t s = m->own_stream;
+  CUDA_TRY(cudaMemcpyAsync(m->d_host_data, h_data, data_floats * sizeof(float), cudaMemcpyHostToDevice, s));
+  MCD_TRY(mcd_reverse_diffusion(m, m->d_host_data, B, G, nullptr, seed, first_window, nullptr, m->d_host_best, nullptr, nullptr,
+                                m->d_host_ws, m->host_ws_bytes, s));
+  CUDA_TRY(cudaMemcpyAsync(h_best, m->d_host_best, size_t(B) * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return MCD_OK;
+}
+
+int64_t mcd_launch_count(const mcd_model* m) { return m ? m->launches.load() : 0; }
+
+int mcd_profile_slots(void) { return SLOT_COUNT; }
+const char* mcd_profile_slot_name(int slot) { return (slot >= 0 && slot < SLOT_COUNT) ? kSlotNames[slot] : ""; }
+
+int mcd_profile_enable(mcd_model* m, int on) {
+  if (m == nullptr) return fail(MCD_ERR_INVALID_ARG, "model handle is NULL");
+  if (on) {
+    CUDA_TRY(cudaSetDevice(m->cfg.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    m->prof_used = 0;
+    for (int i = 0; i < SLOT_COUNT; ++i) { m->prof_ms[i] = 0; m->prof_launches[i] = 0; m->prof_windows[i] = 0; }
+  }
+  m->prof_on = on != 0;
+  return MCD_OK;
+}
+
+int mcd_profile_read(mcd_model* m, double* ms, int64_t* launches, int64_t* windows) {
+  if (m == nullptr) return fail(MCD_ERR_INVALID_ARG, "model handle is NULL");
+  CUDA_TRY(cudaSetDevice(m->cfg.device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  for (size_t i = 0; i < m->prof_used; ++i) {
+    const ProfEvent& e = m->prof_events[i];
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, e.a, e.b));
+    m->prof_ms[e.slot] += t;
+    m->prof_launches[e.slot] += 1;
+    m->prof_windows[e.slot] += e.windows;
+  }
+  m->prof_used = 0;
+  for (int i = 0; i < SLOT_COUNT; ++i) {
+    if (ms) ms[i] = m->prof_ms[i];
+    if (launches) launches[i] = m->prof_launches[i];
+    if (windows) windows[i] = m->prof_windows[i];
+  }
+  return MCD_OK;
+}
+
+int mcd_profile_slot_cost(const mcd_model* m, int slot, double* bytes_per_window, double* flops_per_window) {
+  if (m == nullptr || slot < 0 || slot >= SLOT_COUNT) return fail(MCD_ERR_INVALID_ARG, "mcd_profile_slot_cost: bad argument");
+  double bytes = 0, flops = 0;
+  auto block_cost = [&](int cin, int cout, int T, int V, bool emb, bool cf_in, bool eps_out) {
+    const double P = double(T) * V;
+    bytes = 4.0 * P * (cin + cout) + (eps_out ? 4.0 * P * cout : 0.0);  // in + out (+ the outer-residual read of x)
+    (void)cf_in;
+    flops = 2.0 * cin * P * (T + V) + 2.0 * cin * cout * P * (cin != cout ? 2 : 1) + (emb ? 2.0 * m->E * cout : 0.0);
+  };
+  if (slot < SLOT_RS0) {
+    const BlockShape& b = kUnetBlocks[slot];
+    block_cost(b.cin, b.cout, m->T, kPyramid[b.level], true, slot == 0, slot == kNumUnetBlocks - 1);
+  } else if (slot < SLOT_DDPM) {
+    const ResampleShape& r = kResample[slot - SLOT_RS0];
+    const int vin = kPyramid[r.lin], vout = kPyramid[r.lout];
+    const int C = (slot - SLOT_RS0 == 0 || slot - SLOT_RS0 == 3) ? 32 : 64;
+    const bool skip = (slot - SLOT_RS0) >= 2;
+    bytes = 4.0 * C * m->T * (vin + vout + (skip ? vout : 0));
+    flops = 2.0 * C * m->T * vin * vout;
+  } else if (slot == SLOT_DDPM) {
+    bytes = 4.0 * 2 * m->T * 17 * 3;  // x read+write, eps read (Philox noise costs no bytes)
+    flops = 4.0 * 2 * m->T * 17;
+  } else if (slot == SLOT_RANDN) {
+    bytes = 4.0 * 2 * m->T * 17;
+  } else if (slot == SLOT_LOSS) {
+    bytes = 4.0 * 2 * m->T * 17 * 2 + 4;
+    flops = 4.0 * 2 * m->T * 17;
+  } else if (slot == SLOT_BEST) {
+    bytes = 8;
+  } else if (slot < SLOT_BTLNK) {
+    if (m->Tc > 0) {
+      const int i = slot - SLOT_ENC0;
+      const int chans[kNumEncBlocks + 1] = {2, m->cfg.cond_channels[0], m->cfg.cond_channels[1], m->cfg.cond_channels[2], m->cfg.cond_h_dim};
+      block_cost(chans[i], chans[i + 1], m->Tc, 17, false, i == 0, false);
+    }
+  } else if (slot == SLOT_BTLNK) {
+    bytes = 4.0 * (m->cfg.cond_h_dim * m->Tc * 17 + m->E);
+    flops = 2.0 * m->cfg.cond_h_dim * m->Tc * 17 * m->E;
+  }
+  if (bytes_per_window) *bytes_per_window = bytes;
+  if (flops_per_window) *flops_per_window = flops;
+  return MCD_OK;
+}
+
+int mcd_probe_fp32_tflops(int32_t device, double* tflops) {
+  if (tflops == nullptr) return fail(MCD_ERR_INVALID_ARG, "mcd_probe_fp32_tflops: NULL output");
+  CUDA_TRY(cudaSetDevice(device));
+  int sms = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  float* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, 256));
+  cudaEvent_t a, b;
+  CUDA_TRY(cudaEventCreate(&a));
+  CUDA_TRY(cudaEventCreate(&b));
+  const int iters = 4096, grid = sms * 8;
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_TRY(cudaEventRecord(a));
+    fma_probe_kernel<<<grid, 256>>>(d, iters);
+    CUDA_TRY(cudaEventRecord(b));
+    CUDA_TRY(cudaEventSynchronize(b));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+    const double fl = 2.0 * double(grid) * 256 * iters * 16 * 8;
+    if (rep > 0 && fl / (ms * 1e-3) / 1e12 > best) best = fl / (ms * 1e-3) / 1e12;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  *tflops = best;
+  return MCD_OK;
+}
+
+}  // extern "C"

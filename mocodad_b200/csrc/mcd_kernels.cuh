@@ -1,0 +1,650 @@
+// mcd_kernels.cuh -- sm_100a device code for the MoCoDAD reverse-diffusion scoring path.
+//
+// Data layout in HBM
+//   external tensors (x, eps, noise, data) keep the reference layout  [n][C=2][T][V]  fp32;
+//   activations between denoiser blocks are CHANNEL-LAST              [n][P=T*V][C]   fp32,
+//   so that one (frame,joint) position is a contiguous C-vector: the 1x1 channel convolution
+//   reads it with 128-bit shared loads and both graph mixes are vectorised over channels.
+//
+// Kernels (reference code each one replaces, paths relative to the reference checkout):
+//   stgcn_block_kernel   ST_GCNN_layer.forward, models/gcae/stsgcn.py:94-116 (+ :143-156):
+//                        T-mix -> A-mix -> 1x1 conv (+folded BN) || residual conv -> PReLU -> +emb
+//   joint_resample_kernel CNN_layer over the joint axis (+ U-Net skip add),
+//                        stsgcn.py:187-199 wrapped at models/stsae/stsae_unet.py:205,213,381-394
+//   bottleneck_kernel    STSE.btlnk, models/stsae/stsae.py:52-55,87
+//   ddpm_step_kernel     models/mocodad.py:172-178   (optional counter-based Philox noise)
+//   randn_kernel         models/mocodad.py:162
+//   window_loss_kernel / best_worst_kernel   models/mocodad.py:484-485, 504-512
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mcd {
+
+constexpr int kThreads = 256;
+constexpr int kMaxE = 64;  // embedding_dim upper bound (reference configs use 16)
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src, bool pred) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  int sz = pred ? 16 : 0;  // src-size 0 => the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src, bool pred) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  int sz = pred ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem_src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+__device__ __forceinline__ float f4get(const float4& v, int i) {
+  return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+
+// ------------------------------------------------------------------------------------------
+// Counter-based RNG: Philox4x32-10 (Salmon et al., SC'11) + Box-Muller.
+// One call per element keeps the stream independent of thread mapping, batching and rank count:
+//   counter = (window_lo, window_hi, sample g, slot << 16 | element), key = seed.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t window, uint32_t sample, uint32_t slot,
+                                               uint32_t elem) {
+  uint32_t c0 = static_cast<uint32_t>(window), c1 = static_cast<uint32_t>(window >> 32), c2 = sample;
+  uint32_t c3 = (slot << 16) | (elem & 0xFFFFu);
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  float u1 = (static_cast<float>(c0 >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0,1]
+  float u2 = static_cast<float>(c1 >> 8) * (1.0f / 16777216.0f);          // [0,1)
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+// ------------------------------------------------------------------------------------------
+// ST_GCNN block
+// ------------------------------------------------------------------------------------------
+struct BlockWeights {
+  const float* A;     // [T][V][VP]      gcn.A, rows zero-padded to VP = roundup4(V)
+  const float* Tm;    // [V][TMS]        gcn.T as [v][t*TP4 + q], TMS = T*TP4 + 4
+  const float* Wt;    // [CINP][COUT]    BN-folded tcn conv, transposed (k-major)
+  const float* Wrt;   // [CINP][COUT]    BN-folded residual conv (nullptr: identity residual)
+  const float* bias;  // [COUT]          folded biases (tcn + residual)
+  const float* WEt;   // [E][COUT]       emb_layer.1.weight transposed (nullptr: no embedding)
+  const float* bE;    // [COUT]
+  float prelu;        // prelu.weight[0]
+};
+
+struct BlockIO {
+  const float* in;    // channel-last [n][P][CIN]  (IN_CL)  or channel-first source (IN_CF)
+  float* out;         // channel-last [n][P][COUT] (OUT_CL) or [n][2][P] eps      (OUT_EPS)
+  int64_t n;          // windows
+  int64_t in_sn;      // IN_CF: element (w,c,t,v) = in[w*in_sn + c*in_sc + (t+in_t0)*V + v]
+  int32_t in_sc, in_t0;
+  const float* xres;  // OUT_EPS: eps = out + xres (the U-Net input, stsae_unet.py:401); nullptr: no add
+  const float* pos;   // [E] pos_encoding(t) of this step
+  const float* cond;  // [condB][E] conditioning embedding (nullptr: none); window w uses row (w0+w) % condB
+  int64_t condB;
+  int64_t w0;         // virtual index of window 0 of this launch
+  int32_t E;
+};
+
+enum { IN_CL = 0, IN_CF = 1 };
+enum { OUT_CL = 0, OUT_EPS = 1 };
+
+template <int T_, int V_, int CIN_, int COUT_, int NW_, bool EMB_, int INMODE_, int OUTMODE_>
+struct BlockCfg {
+  static constexpr int T = T_, V = V_, CIN = CIN_, COUT = COUT_, NW = NW_;
+  static constexpr bool EMB = EMB_;
+  static constexpr int INMODE = INMODE_, OUTMODE = OUTMODE_;
+  static constexpr int P = T * V;
+  static constexpr int ROWS = NW * P;                 // (window, frame, joint) rows per tile
+  static constexpr int CINP = CIN < 4 ? 4 : CIN;      // input channels padded to a float4
+  static constexpr int KC = CINP < 16 ? CINP : 16;    // channels per pipeline chunk
+  static constexpr int NCHUNK = CINP / KC;
+  static constexpr int C4 = KC / 4;
+  static constexpr int CP = KC + 4;                   // smem row stride (floats): conflict-free conv reads
+  static constexpr int VP = (V + 3) / 4 * 4;
+  static constexpr int TP4 = (T + 3) / 4 * 4;
+  static constexpr int TMS = T * TP4 + 4;
+  static constexpr bool RESCONV = CIN != COUT;
+  // 1x1 conv register tile: TPR rows x TCO output channels per thread
+  static constexpr int TCO = COUT >= 128 ? 16 : (COUT >= 8 ? 8 : COUT);
+  static constexpr int NCG = COUT / TCO;
+  static constexpr int NPG = kThreads / NCG;
+  static constexpr int TPR = (ROWS + NPG - 1) / NPG;
+  // T-mix tile: 4 channels x TQ output frames;  A-mix tile: 4 channels x TW output joints
+  static constexpr int TQ = TP4 <= 8 ? TP4 : 8;
+  static constexpr int NQT = TP4 / TQ;
+  static constexpr int NWT = 2;
+  static constexpr int TW = VP / NWT;
+  static_assert(TP4 % TQ == 0 && VP % (2 * NWT) == 0, "tile shapes");
+  static_assert(CINP % KC == 0 && COUT % TCO == 0 && kThreads % NCG == 0, "channel tiling");
+  static_assert(RESCONV || (TCO <= KC && KC % TCO == 0), "identity residual needs the co-tile inside one chunk");
+  // shared memory carve-up (floats)
+  static constexpr int SM_A = 0;
+  static constexpr int SM_TM = SM_A + T * V * VP;
+  static constexpr int SM_W = SM_TM + V * TMS;
+  static constexpr int SM_WR = SM_W + CINP * COUT;
+  static constexpr int SM_BIAS = SM_WR + (RESCONV ? CINP * COUT : 0);
+  static constexpr int SM_EMB = SM_BIAS + COUT;
+  static constexpr int SM_S = SM_EMB + NW * COUT;
+  static constexpr int SM_X = (SM_S + NW * kMaxE + 3) / 4 * 4;
+  static constexpr int SM_Y1 = SM_X + 2 * ROWS * CP;
+  static constexpr int SM_Y2 = SM_Y1 + ROWS * CP;
+  static constexpr int SM_TOTAL = SM_Y2 + ROWS * CP;
+  static constexpr size_t SMEM_BYTES = size_t(SM_TOTAL) * sizeof(float);
+};
+
+template <class Cfg>
+__device__ __forceinline__ void block_prefetch(const BlockIO& io, float* sXbuf, int64_t tile, int chunk, int tid) {
+  constexpr int ROWS = Cfg::ROWS, CP = Cfg::CP, C4 = Cfg::C4, P = Cfg::P;
+  if constexpr (Cfg::INMODE == IN_CL) {
+    const int64_t row0 = tile * ROWS;
+    const int64_t nrows = io.n * P;
+    const float* base = io.in + chunk * Cfg::KC;
+    for (int idx = tid; idx < ROWS * C4; idx += kThreads) {
+      int r = idx / C4, j = idx - r * C4;
+      bool ok = (row0 + r) < nrows;
+      const float* src = ok ? base + (row0 + r) * Cfg::CIN + j * 4 : io.in;
+      cp_async16(sXbuf + r * CP + j * 4, src, ok);
+    }
+  } else {  // channel-first, CIN real channels (2), padded channels stay zero (set once at start)
+    for (int idx = tid; idx < ROWS * Cfg::CIN; idx += kThreads) {
+      int c = idx / ROWS, r = idx - c * ROWS;
+      int wl = r / P, p = r - wl * P;
+      int64_t w = tile * Cfg::NW + wl;
+      bool ok = w < io.n;
+      const float* src = ok ? io.in + w * io.in_sn + int64_t(c) * io.in_sc + io.in_t0 * Cfg::V + p : io.in;
+      cp_async4(sXbuf + r * CP + c, src, ok);
+    }
+  }
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(kThreads, 1) stgcn_block_kernel(const BlockWeights wt, const BlockIO io) {
+  constexpr int T = Cfg::T, V = Cfg::V, P = Cfg::P, ROWS = Cfg::ROWS, CP = Cfg::CP, C4 = Cfg::C4;
+  constexpr int COUT = Cfg::COUT, CINP = Cfg::CINP, KC = Cfg::KC, NCHUNK = Cfg::NCHUNK;
+  constexpr int VP = Cfg::VP, TP4 = Cfg::TP4, TMS = Cfg::TMS, NW = Cfg::NW;
+  constexpr int TCO = Cfg::TCO, NCG = Cfg::NCG, NPG = Cfg::NPG, TPR = Cfg::TPR;
+  constexpr int TQ = Cfg::TQ, NQT = Cfg::NQT, TW = Cfg::TW, NWT = Cfg::NWT;
+  constexpr bool RESCONV = Cfg::RESCONV;
+
+  extern __shared__ __align__(16) float smem[];
+  float* sA = smem + Cfg::SM_A;
+  float* sTm = smem + Cfg::SM_TM;
+  float* sW = smem + Cfg::SM_W;
+  float* sWr = smem + Cfg::SM_WR;
+  float* sBias = smem + Cfg::SM_BIAS;
+  float* sEmb = smem + Cfg::SM_EMB;
+  float* sS = smem + Cfg::SM_S;
+  float* sX = smem + Cfg::SM_X;
+  float* sY1 = smem + Cfg::SM_Y1;
+  float* sY2 = smem + Cfg::SM_Y2;
+
+  const int tid = threadIdx.x;
+  const int64_t ntiles = (io.n + NW - 1) / NW;
+  if (int64_t(blockIdx.x) >= ntiles) return;
+
+  // ---- once per CTA: weights -> smem (persistent over all tiles of this CTA) ----
+  for (int i = tid; i < T * V * VP; i += kThreads) sA[i] = wt.A[i];
+  for (int i = tid; i < V * TMS; i += kThreads) sTm[i] = wt.Tm[i];
+  for (int i = tid; i < CINP * COUT; i += kThreads) sW[i] = wt.Wt[i];
+  if constexpr (RESCONV)
+    for (int i = tid; i < CINP * COUT; i += kThreads) sWr[i] = wt.Wrt[i];
+  for (int i = tid; i < COUT; i += kThreads) sBias[i] = wt.bias[i];
+  if constexpr (Cfg::INMODE == IN_CF)
+    for (int i = tid; i < 2 * ROWS * CP; i += kThreads) sX[i] = 0.f;
+  __syncthreads();
+
+  // conv register tile of this thread
+  const int cg = tid % NCG, pg = tid / NCG;
+  float acc[TPR][TCO];
+#pragma unroll
+  for (int i = 0; i < TPR; ++i)
+#pragma unroll
+    for (int j = 0; j < TCO; ++j) acc[i][j] = 0.f;
+
+  // flattened (tile, chunk) pipeline: the next pair streams in while this one is computed
+  const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const int64_t npairs = my_tiles * NCHUNK;
+  block_prefetch<Cfg>(io, sX, blockIdx.x, 0, tid);
+  cp_async_commit();
+
+  for (int64_t it = 0; it < npairs; ++it) {
+    const int64_t tile = blockIdx.x + (it / NCHUNK) * gridDim.x;
+    const int chunk = int(it % NCHUNK);
+    const int kc0 = chunk * KC;
+    float* sXc = sX + (it & 1) * ROWS * CP;
+
+    cp_async_wait_all();
+    __syncthreads();  // X chunk visible; everyone is done with the previous pair's buffers
+    if (it + 1 < npairs) {
+      const int64_t ntile = blockIdx.x + ((it + 1) / NCHUNK) * gridDim.x;
+      block_prefetch<Cfg>(io, sX + ((it + 1) & 1) * ROWS * CP, ntile, int((it + 1) % NCHUNK), tid);
+      cp_async_commit();
+    }
+
+    // ---- per-tile: time/condition embedding  emb = Linear(SiLU(pos + cond)), stsgcn.py:112-114
+    if constexpr (Cfg::EMB) {
+      if (chunk == 0) {
+        const int E = io.E;
+        for (int i = tid; i < NW * E; i += kThreads) {
+          int wl = i / E, j = i - wl * E;
+          int64_t w = tile * NW + wl;
+          float v = io.pos[j];
+          if (io.cond != nullptr && w < io.n) v += io.cond[((io.w0 + w) % io.condB) * E + j];
+          sS[wl * kMaxE + j] = v / (1.0f + expf(-v));
+        }
+      }
+    }
+
+    // ---- phase 1: T-mix   Y1[n,(q,v),c] = sum_t X[n,(t,v),c] * Tm[v][t][q]     stsgcn.py:154
+    for (int task = tid; task < NQT * NW * V * C4; task += kThreads) {
+      const int c4 = task % C4;
+      const int col = (task / C4) % (NW * V);  // (window-in-tile, joint)
+      const int qt = task / (C4 * NW * V);
+      const int wl = col / V, v = col - wl * V;
+      float a[4][TQ];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int q = 0; q < TQ; ++q) a[c][q] = 0.f;
+      const float* xp = sXc + (wl * P + v) * CP + c4 * 4;
+      const float* tp = sTm + v * TMS + qt * TQ;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const float4 x = *reinterpret_cast<const float4*>(xp + t * V * CP);
+#pragma unroll
+        for (int q4 = 0; q4 < TQ / 4; ++q4) {
+          const float4 w = *reinterpret_cast<const float4*>(tp + t * TP4 + q4 * 4);
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const float wv = f4get(w, qq);
+            a[0][q4 * 4 + qq] = fmaf(x.x, wv, a[0][q4 * 4 + qq]);
+            a[1][q4 * 4 + qq] = fmaf(x.y, wv, a[1][q4 * 4 + qq]);
+            a[2][q4 * 4 + qq] = fmaf(x.z, wv, a[2][q4 * 4 + qq]);
+            a[3][q4 * 4 + qq] = fmaf(x.w, wv, a[3][q4 * 4 + qq]);
+          }
+        }
+      }
+      float* yp = sY1 + (wl * P + v) * CP + c4 * 4;
+#pragma unroll
+      for (int q = 0; q < TQ; ++q) {
+        const int qq = qt * TQ + q;
+        if (qq < T) *reinterpret_cast<float4*>(yp + qq * V * CP) = make_float4(a[0][q], a[1][q], a[2][q], a[3][q]);
+      }
+    }
+    if constexpr (Cfg::EMB) {
+      if (chunk == 0) {
+        __syncthreads();  // sS complete (rare path: once per tile)
+        const int E = io.E;
+        for (int i = tid; i < NW * COUT; i += kThreads) {
+          int wl = i / COUT, co = i - wl * COUT;
+          float e = wt.bE[co];
+          for (int j = 0; j < E; ++j) e = fmaf(wt.WEt[j * COUT + co], sS[wl * kMaxE + j], e);
+          sEmb[i] = e;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 2: A-mix   Y2[n,(t,w),c] = sum_v Y1[n,(t,v),c] * A[t][v][w]      stsgcn.py:155
+    for (int task = tid; task < NW * T * NWT * C4; task += kThreads) {
+      const int c4 = task % C4;
+      const int wtile = (task / C4) % NWT;
+      const int row = task / (C4 * NWT);  // (window-in-tile, frame)
+      const int wl = row / T, q = row - wl * T;
+      float a[4][TW];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int j = 0; j < TW; ++j) a[c][j] = 0.f;
+      const float* yp = sY1 + (wl * P + q * V) * CP + c4 * 4;
+      const float* ap = sA + q * V * VP + wtile * TW;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float4 y = *reinterpret_cast<const float4*>(yp + v * CP);
+#pragma unroll
+        for (int j2 = 0; j2 < TW / 2; ++j2) {
+          const float2 w = *reinterpret_cast<const float2*>(ap + v * VP + j2 * 2);
+          a[0][j2 * 2] = fmaf(y.x, w.x, a[0][j2 * 2]);
+          a[1][j2 * 2] = fmaf(y.y, w.x, a[1][j2 * 2]);
+          a[2][j2 * 2] = fmaf(y.z, w.x, a[2][j2 * 2]);
+          a[3][j2 * 2] = fmaf(y.w, w.x, a[3][j2 * 2]);
+          a[0][j2 * 2 + 1] = fmaf(y.x, w.y, a[0][j2 * 2 + 1]);
+          a[1][j2 * 2 + 1] = fmaf(y.y, w.y, a[1][j2 * 2 + 1]);
+          a[2][j2 * 2 + 1] = fmaf(y.z, w.y, a[2][j2 * 2 + 1]);
+          a[3][j2 * 2 + 1] = fmaf(y.w, w.y, a[3][j2 * 2 + 1]);
+        }
+      }
+      float* zp = sY2 + (wl * P + q * V) * CP + c4 * 4;
+#pragma unroll
+      for (int j = 0; j < TW; ++j) {
+        const int w = wtile * TW + j;
+        if (w < V) *reinterpret_cast<float4*>(zp + w * CP) = make_float4(a[0][j], a[1][j], a[2][j], a[3][j]);
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 3: 1x1 conv accumulate  acc[r][co] += Y2[r][k]*W[k][co] (+ X[r][k]*Wr[k][co])
+    {
+      int rows[TPR];
+#pragma unroll
+      for (int i = 0; i < TPR; ++i) {
+        int r = pg + i * NPG;
+        rows[i] = r < ROWS ? r : ROWS - 1;  // clamp: padded slots recompute the last row, never stored
+      }
+#pragma unroll
+      for (int k4 = 0; k4 < C4; ++k4) {
+        float4 yv[TPR];
+#pragma unroll
+        for (int i = 0; i < TPR; ++i) yv[i] = *reinterpret_cast<const float4*>(sY2 + rows[i] * CP + k4 * 4);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          float w[TCO];
+          const float* wp = sW + (kc0 + k4 * 4 + kk) * COUT + cg * TCO;
+          if constexpr (TCO % 4 == 0) {
+#pragma unroll
+            for (int j4 = 0; j4 < TCO / 4; ++j4) {
+              const float4 t4 = *reinterpret_cast<const float4*>(wp + j4 * 4);
+              w[j4 * 4] = t4.x; w[j4 * 4 + 1] = t4.y; w[j4 * 4 + 2] = t4.z; w[j4 * 4 + 3] = t4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < TCO; ++j) w[j] = wp[j];
+          }
+#pragma unroll
+          for (int i = 0; i < TPR; ++i) {
+            const float y = f4get(yv[i], kk);
+#pragma unroll
+            for (int j = 0; j < TCO; ++j) acc[i][j] = fmaf(y, w[j], acc[i][j]);
+          }
+        }
+        if constexpr (RESCONV) {
+#pragma unroll
+          for (int i = 0; i < TPR; ++i) yv[i] = *reinterpret_cast<const float4*>(sXc + rows[i] * CP + k4 * 4);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            float w[TCO];
+            const float* wp = sWr + (kc0 + k4 * 4 + kk) * COUT + cg * TCO;
+            if constexpr (TCO % 4 == 0) {
+#pragma unroll
+              for (int j4 = 0; j4 < TCO / 4; ++j4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(wp + j4 * 4);
+                w[j4 * 4] = t4.x; w[j4 * 4 + 1] = t4.y; w[j4 * 4 + 2] = t4.z; w[j4 * 4 + 3] = t4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < TCO; ++j) w[j] = wp[j];
+            }
+#pragma unroll
+            for (int i = 0; i < TPR; ++i) {
+              const float y = f4get(yv[i], kk);
+#pragma unroll
+              for (int j = 0; j < TCO; ++j) acc[i][j] = fmaf(y, w[j], acc[i][j]);
+            }
+          }
+        }
+      }
+      if constexpr (!RESCONV) {  // identity residual: this thread's co-tile lives in exactly one chunk
+        if ((cg * TCO) / KC == chunk) {
+          const int off = cg * TCO - kc0;
+#pragma unroll
+          for (int i = 0; i < TPR; ++i)
+#pragma unroll
+            for (int j = 0; j < TCO; ++j) acc[i][j] += sXc[rows[i] * CP + off + j];
+        }
+      }
+
+      // ---- epilogue on the last chunk: bias, PReLU, +emb, store                stsgcn.py:109-114
+      if (chunk == NCHUNK - 1) {
+        const float slope = wt.prelu;
+#pragma unroll
+        for (int i = 0; i < TPR; ++i) {
+          const int r = pg + i * NPG;
+          const int wl = r / P;
+          const int64_t w = tile * NW + wl;
+          const bool ok = (r < ROWS) && (w < io.n);
+          float o[TCO];
+#pragma unroll
+          for (int j = 0; j < TCO; ++j) {
+            const int co = cg * TCO + j;
+            float v = acc[i][j] + sBias[co];
+            v = v > 0.f ? v : slope * v;
+            if constexpr (Cfg::EMB) v += sEmb[(ok ? wl : 0) * COUT + co];
+            o[j] = v;
+            acc[i][j] = 0.f;
+          }
+          if (ok) {
+            if constexpr (Cfg::OUTMODE == OUT_CL) {
+              float* dst = io.out + (tile * ROWS + r) * COUT + cg * TCO;
+              if constexpr (TCO % 4 == 0) {
+#pragma unroll
+                for (int j4 = 0; j4 < TCO / 4; ++j4)
+                  *reinterpret_cast<float4*>(dst + j4 * 4) = make_float4(o[j4 * 4], o[j4 * 4 + 1], o[j4 * 4 + 2], o[j4 * 4 + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < TCO; ++j) dst[j] = o[j];
+              }
+            } else {  // OUT_EPS: reference layout [n][COUT][P], plus the U-Net's outer residual +X
+              const int p = r - wl * P;
+#pragma unroll
+              for (int j = 0; j < TCO; ++j) {
+                const int64_t e = (w * COUT + (cg * TCO + j)) * P + p;
+                io.out[e] = io.xres != nullptr ? o[j] + io.xres[e] : o[j];
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Joint-axis resample (CNN_layer + folded BN) with optional skip add.  Memory-bound.
+//   out[n,(t,w),c] = b'[w] + sum_v Wd'[w][v] * in[n,(t,v),c]  (+ skip[n,(t,w),c])
+// One thread per (window, frame, 4 channels).
+// ------------------------------------------------------------------------------------------
+template <int VIN, int VOUT>
+__global__ void __launch_bounds__(kThreads) joint_resample_kernel(const float* __restrict__ in,
+                                                                   const float* __restrict__ skip,
+                                                                   float* __restrict__ out,
+                                                                   const float* __restrict__ Wd,  // [VOUT][VIN]
+                                                                   const float* __restrict__ bd,  // [VOUT]
+                                                                   int64_t n_frames_total,        // n * T
+                                                                   int C) {
+  __shared__ float sWd[VOUT * VIN];
+  __shared__ float sb[VOUT];
+  for (int i = threadIdx.x; i < VOUT * VIN; i += kThreads) sWd[i] = Wd[i];
+  for (int i = threadIdx.x; i < VOUT; i += kThreads) sb[i] = bd[i];
+  __syncthreads();
+  const int c4n = C / 4;
+  const int64_t total = n_frames_total * c4n;
+  for (int64_t idx = blockIdx.x * int64_t(kThreads) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * kThreads) {
+    const int64_t f = idx / c4n;
+    const int c4 = int(idx - f * c4n);
+    const float* ip = in + (f * VIN) * C + c4 * 4;
+    float4 x[VIN];
+#pragma unroll
+    for (int v = 0; v < VIN; ++v) x[v] = *reinterpret_cast<const float4*>(ip + int64_t(v) * C);
+    float* op = out + (f * VOUT) * C + c4 * 4;
+    const float* sp = skip ? skip + (f * VOUT) * C + c4 * 4 : nullptr;
+#pragma unroll
+    for (int w = 0; w < VOUT; ++w) {
+      float4 a = make_float4(sb[w], sb[w], sb[w], sb[w]);
+#pragma unroll
+      for (int v = 0; v < VIN; ++v) {
+        const float k = sWd[w * VIN + v];
+        a.x = fmaf(k, x[v].x, a.x); a.y = fmaf(k, x[v].y, a.y);
+        a.z = fmaf(k, x[v].z, a.z); a.w = fmaf(k, x[v].w, a.w);
+      }
+      if (sp) {
+        const float4 s = *reinterpret_cast<const float4*>(sp + int64_t(w) * C);
+        a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w;
+      }
+      *reinterpret_cast<float4*>(op + int64_t(w) * C) = a;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Bottleneck linear of the conditioning encoder: emb[n][l] = b[l] + sum_k h[n][k] * Wb[k][l]
+// h is channel-last [n][P*C]; Wb was re-indexed at pack time to that order.  One warp / window.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) bottleneck_kernel(const float* __restrict__ h, const float* __restrict__ Wb,
+                                                              const float* __restrict__ bb, float* __restrict__ out,
+                                                              int64_t n, int K, int L) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (blockIdx.x * int64_t(kThreads) + threadIdx.x) >> 5;
+  if (w >= n) return;
+  float acc[kMaxE];
+#pragma unroll
+  for (int l = 0; l < kMaxE; ++l) acc[l] = 0.f;
+  const float* hp = h + w * K;
+  for (int k = lane; k < K; k += 32) {
+    const float x = hp[k];
+    const float* wp = Wb + int64_t(k) * L;
+#pragma unroll
+    for (int l = 0; l < kMaxE; ++l)
+      if (l < L) acc[l] = fmaf(x, wp[l], acc[l]);
+  }
+#pragma unroll
+  for (int l = 0; l < kMaxE; ++l) {
+    if (l < L) {
+      float v = acc[l];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) out[w * L + l] = v + bb[l];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// DDPM update (mocodad.py:178), elementwise, in place.  The arithmetic keeps the reference's
+// operation order with explicit round-to-nearest ops (no FMA contraction) so that with injected
+// noise the update is bit-faithful to eager PyTorch.
+//   noise: pre-drawn tensor addressed as noise[(g*slots + slot)*B + b][2P] for virtual window
+//   w = g*B + b (pass B = n, g = 0 for a plain [n,2P] tensor), or nullptr => Philox.
+// ------------------------------------------------------------------------------------------
+struct DdpmArgs {
+  float c1, c2, c3;       // 1/sqrt(alpha_t), (1-alpha_t)/sqrt(1-alpha_hat_t), sqrt(beta_t)
+  int add_noise;          // 0 at t == 1
+  const float* noise;     // nullptr => Philox
+  int64_t noise_B;        // windows per sample B: virtual index = g*B + b (always set)
+  int32_t noise_slots;    // N-1
+  int32_t slot;           // which slot this step reads / Philox slot id
+  int64_t virt0;          // virtual index of window 0 of this call (for noise addressing)
+  uint64_t seed;
+  int64_t first_window;   // global (dataset) id of window b = 0 (Philox counter base)
+};
+
+__global__ void __launch_bounds__(kThreads) ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ eps,
+                                                             int64_t n, int per_window, DdpmArgs a) {
+  const int64_t total = n * per_window;
+  for (int64_t i = blockIdx.x * int64_t(kThreads) + threadIdx.x; i < total; i += int64_t(gridDim.x) * kThreads) {
+    const int64_t w = i / per_window;
+    const int e = int(i - w * per_window);
+    float z = 0.f;
+    if (a.add_noise) {
+      const int64_t virt = a.virt0 + w;
+      if (a.noise != nullptr) {
+        const int64_t g = virt / a.noise_B, b = virt - g * a.noise_B;
+        z = a.noise[((g * a.noise_slots + a.slot) * a.noise_B + b) * per_window + e];
+      } else {
+        const int64_t g = virt / a.noise_B, b = virt - g * a.noise_B;
+        z = philox_normal(a.seed, uint64_t(a.first_window + b), uint32_t(g), uint32_t(a.slot), uint32_t(e));
+      }
+    }
+    const float t1 = __fmul_rn(a.c2, eps[i]);
+    const float t2 = __fsub_rn(x[i], t1);
+    const float t3 = __fmul_rn(a.c1, t2);
+    const float t4 = __fmul_rn(a.c3, z);
+    x[i] = __fadd_rn(t3, t4);
+  }
+}
+
+// x_T: from the pre-drawn tensor (slot 0) or Philox (slot 0).  mocodad.py:162
+__global__ void __launch_bounds__(kThreads) randn_kernel(float* __restrict__ x, int64_t n, int per_window, DdpmArgs a) {
+  const int64_t total = n * per_window;
+  for (int64_t i = blockIdx.x * int64_t(kThreads) + threadIdx.x; i < total; i += int64_t(gridDim.x) * kThreads) {
+    const int64_t w = i / per_window;
+    const int e = int(i - w * per_window);
+    const int64_t virt = a.virt0 + w;
+    float z;
+    if (a.noise != nullptr) {
+      const int64_t g = virt / a.noise_B, b = virt - g * a.noise_B;
+      z = a.noise[((g * a.noise_slots + a.slot) * a.noise_B + b) * per_window + e];
+    } else {
+      const int64_t g = virt / a.noise_B, b = virt - g * a.noise_B;
+      z = philox_normal(a.seed, uint64_t(a.first_window + b), uint32_t(g), uint32_t(a.slot), uint32_t(e));
+    }
+    x[i] = z;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-window loss: mean over (C,T,V) of the elementwise loss between the generated sample and
+// the corrupt frames of the input window (mocodad.py:484).  One warp per virtual window.
+//   x0 [nv][2][P];  data [B][2][n_frames][V], target frames start at t0;  virtual w -> b = (virt0+w) % B
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) window_loss_kernel(const float* __restrict__ x0, const float* __restrict__ data,
+                                                               float* __restrict__ losses, int64_t nv, int64_t virt0,
+                                                               int64_t B, int P, int V, int n_frames, int t0, int loss_fn) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (blockIdx.x * int64_t(kThreads) + threadIdx.x) >> 5;
+  if (w >= nv) return;
+  const int64_t b = (virt0 + w) % B;
+  const float* xp = x0 + w * 2 * P;
+  const float* dp = data + b * 2 * int64_t(n_frames) * V + int64_t(t0) * V;
+  float s = 0.f;
+  for (int e = lane; e < 2 * P; e += 32) {
+    const int c = e / P, p = e - c * P;
+    const float d = xp[e] - dp[int64_t(c) * n_frames * V + p];
+    const float ad = fabsf(d);
+    float l;
+    if (loss_fn == 0) l = ad < 1.0f ? 0.5f * d * d : ad - 0.5f;  // SmoothL1, beta = 1
+    else if (loss_fn == 1) l = ad;
+    else l = d * d;
+    s += l;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) losses[w] = s / float(2 * P);
+}
+
+// 'best' / 'worst' over the G samples (mocodad.py:504-512): strict compare against 1e10 / -1.
+__global__ void __launch_bounds__(kThreads) best_worst_kernel(const float* __restrict__ losses, float* __restrict__ best,
+                                                              float* __restrict__ worst, int64_t B, int G) {
+  const int64_t b = blockIdx.x * int64_t(kThreads) + threadIdx.x;
+  if (b >= B) return;
+  float lo = 1e10f, hi = -1.0f;
+  for (int g = 0; g < G; ++g) {
+    const float l = losses[int64_t(g) * B + b];
+    if (l < lo) lo = l;
+    if (l > hi) hi = l;
+  }
+  if (best) best[b] = lo;
+  if (worst) worst[b] = hi;
+}
+
+// channel-last [n][P][C] -> reference layout [n][C][P]  (parity taps only)
+__global__ void __launch_bounds__(kThreads) cl_to_cf_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                            int64_t n, int P, int C) {
+  const int64_t total = n * P * C;
+  for (int64_t i = blockIdx.x * int64_t(kThreads) + threadIdx.x; i < total; i += int64_t(gridDim.x) * kThreads) {
+    const int64_t w = i / (int64_t(P) * C);
+    const int rem = int(i - w * P * C);
+    const int c = rem / P, p = rem - c * P;
+    out[i] = in[(w * P + p) * C + c];
+  }
+}
+
+}  // namespace mcd

@@ -1,0 +1,283 @@
+"""Torch-facing wrapper over the C ABI: owns one ``mcd_model`` handle and hands the library raw
+device pointers of torch tensors plus the current CUDA stream.  PyTorch is used here for device
+memory and streams only -- every number is produced by the CUDA library (``_lib.load()`` raises
+if it is absent; there is no other implementation).
+
+Reference being replaced: the body of ``MoCoDAD.forward`` (models/mocodad.py:129-184) and the
+modules under it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Mapping, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import McdConfig, check
+
+N_JOINTS = 17
+N_COORDS = 2
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class ScoringEngine:
+    """One reverse-diffusion scorer on one CUDA device.
+
+    Args mirror the fields ``MoCoDAD.__init__`` reads from the YAML namespace (mocodad.py:46-81):
+    ``seg_len``, number of conditioning frames and whether they come first, ``noise_steps``,
+    ``loss_fn``, ``embedding_dim`` (== ``latent_dim``), ``h_dim``, ``channels``.
+    """
+
+    def __init__(self, *, seg_len: int, n_frames_cond: int, cond_first: bool = True, noise_steps: int,
+                 loss_fn: str = "smooth_l1", embedding_dim: int = 16, h_dim: int = 32,
+                 channels: Sequence[int] = (32, 16, 32), device="cuda:0", n_joints: int = N_JOINTS,
+                 num_coords: int = N_COORDS):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError(f"ScoringEngine needs a CUDA device (got {self.device}); there is no CPU path")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        if loss_fn not in _lib.LOSS_FN:
+            raise ValueError(f"unknown loss_fn {loss_fn!r}")
+        ch = list(channels) + [0, 0, 0]
+        self.cfg = McdConfig(n_coords=num_coords, n_joints=n_joints, n_frames=seg_len, n_frames_cond=n_frames_cond,
+                             cond_first=int(bool(cond_first)), embedding_dim=embedding_dim, cond_h_dim=h_dim,
+                             cond_channels=(C.c_int32 * 3)(*ch[:3]), noise_steps=noise_steps,
+                             loss_fn=_lib.LOSS_FN[loss_fn], device=self.device.index)
+        if n_frames_cond > 0 and len(channels) != 3:
+            raise _lib.McdError(-2, f"conditioning encoder with {len(channels)} hidden layers (kernels are built for 3)")
+        handle = C.c_void_p()
+        check(self.lib.mcd_model_create(C.byref(self.cfg), C.byref(handle)))
+        self._h = handle
+        self.seg_len, self.n_cond, self.T = seg_len, n_frames_cond, seg_len - n_frames_cond
+        self.N, self.E = noise_steps, embedding_dim
+        self.finalized = False
+        self._ws: Optional[torch.Tensor] = None
+        props = torch.cuda.get_device_properties(self.device)
+        self.num_sms = props.multi_processor_count
+        self.tile_unit = self.num_sms * max(1, 408 // (self.T * N_JOINTS))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None and h.value:
+            try:
+                self.lib.mcd_model_destroy(h)
+            except Exception:
+                pass
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, sd: Mapping[str, torch.Tensor]) -> None:
+        """Stream a reference ``state_dict`` (any superset of the needed entries) into the handle,
+        fold BatchNorm / re-lay weights, upload.  Replaces build_model + load_state_dict."""
+        keep = []
+        for name, t in sd.items():
+            if not torch.is_tensor(t) or not t.dtype.is_floating_point:
+                continue  # num_batches_tracked
+            h = t.detach().to("cpu", torch.float32).contiguous()
+            keep.append(h)
+            check(self.lib.mcd_model_set_tensor(self._h, name.encode(), h.data_ptr(), h.numel()))
+        with torch.cuda.device(self.device):
+            check(self.lib.mcd_model_finalize(self._h))
+        self.finalized = True
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _chk(self, t: torch.Tensor, shape: Tuple[int, ...], name: str) -> torch.Tensor:
+        if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError(f"{name}: need a contiguous float32 tensor on {self.device} "
+                             f"(got {t.dtype}, {t.device}, contiguous={t.is_contiguous()})")
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    def workspace_bytes(self, n: int) -> int:
+        return int(self.lib.mcd_workspace_bytes(self._h, int(n)))
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _new(self, *shape) -> torch.Tensor:
+        return torch.empty(*shape, dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------ single ops (parity surface)
+    def cond_encode(self, data: torch.Tensor) -> torch.Tensor:
+        """MoCoDAD._encode_condition (mocodad.py:546-560) on whole windows [B,2,seg_len,V] -> [B,E]."""
+        B = data.shape[0]
+        self._chk(data, (B, N_COORDS, self.seg_len, N_JOINTS), "data")
+        out = self._new(B, self.E)
+        ws = self._workspace(self.workspace_bytes(max(B, 1)))
+        with torch.cuda.device(self.device):
+            check(self.lib.mcd_cond_encode(self._h, data.data_ptr(), B, out.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()))
+        return out
+
+    def unet_forward(self, x: torch.Tensor, t: int, cond_emb: Optional[torch.Tensor]) -> torch.Tensor:
+        """STSAE_Unet.forward (stsae_unet.py:406-438): predicted noise for x [n,2,T,V] at step t."""
+        n = x.shape[0]
+        self._chk(x, (n, N_COORDS, self.T, N_JOINTS), "x")
+        cb = 0
+        if cond_emb is not None:
+            cb = cond_emb.shape[0]
+            self._chk(cond_emb, (cb, self.E), "cond_emb")
+        eps = torch.empty_like(x)
+        ws = self._workspace(self.workspace_bytes(max(n, 1)))
+        with torch.cuda.device(self.device):
+            check(self.lib.mcd_unet_forward(self._h, x.data_ptr(), n, int(t), _ptr(cond_emb), cb, eps.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), self._stream()))
+        return eps
+
+    def unet_tap(self, x: torch.Tensor, t: int, cond_emb: Optional[torch.Tensor], layer: str,
+                 channels: int, joints: int) -> torch.Tensor:
+        n = x.shape[0]
+        self._chk(x, (n, N_COORDS, self.T, N_JOINTS), "x")
+        cb = 0 if cond_emb is None else cond_emb.shape[0]
+        out = self._new(n, channels, self.T, joints)
+        ws = self._workspace(self.workspace_bytes(max(n, 1)))
+        with torch.cuda.device(self.device):
+            check(self.lib.mcd_unet_tap(self._h, x.data_ptr(), n, int(t), _ptr(cond_emb), cb, layer.encode(),
+                                        out.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()))
+        return out
+
+    def ddpm_step(self, x: torch.Tensor, eps: torch.Tensor, t: int, noise: Optional[torch.Tensor] = None, *,
+                  seed: int = 0, first_window: int = 0, sample: int = 0, noise_slot: int = 0) -> torch.Tensor:
+        """In-place DDPM update of x (mocodad.py:172-178).  Returns x."""
+        n = x.shape[0]
+        shape = (n, N_COORDS, self.T, N_JOINTS)
+        self._chk(x, shape, "x"); self._chk(eps, shape, "eps")
+        if noise is not None:
+            self._chk(noise, shape, "noise")
+        with torch.cuda.device(self.device):
+            check(self.lib.mcd_ddpm_step(self._h, x.data_ptr(), eps.data_ptr(), _ptr(noise), n, int(t), int(seed),
+                                         int(first_window), int(sample), int(noise_slot), self._stream()))
+        return x
+
+    def randn_windows(self, n: int, *, seed: int, first_window: int = 0, sample: int = 0, noise_slot: int = 0) -> torch.Tensor:
+        x = self._new(n, N_COORDS, self.T, N_JOINTS)
+        with torch.cuda.device(self.device):
+            check(self.lib.mcd_randn_windows(self._h, x.data_ptr(), n, int(seed), int(first_window), int(sample),
+                                             int(noise_slot), self._stream()))
+        return x
+
+    def window_loss(self, x0: torch.Tensor, data: torch.Tensor, G: int = 1) -> Dict[str, torch.Tensor]:
+        """Per-window loss of G samples against the corrupt frames of ``data`` + best/worst over G."""
+        B = data.shape[0]
+        self._chk(data, (B, N_COORDS, self.seg_len, N_JOINTS), "data")
+        self._chk(x0.reshape(G * B, N_COORDS, self.T, N_JOINTS), (G * B, N_COORDS, self.T, N_JOINTS), "x0")
+        losses, best, worst = self._new(G, B), self._new(B), self._new(B)
+        with torch.cuda.device(self.device):
+            check(self.lib.mcd_window_loss(self._h, x0.data_ptr(), data.data_ptr(), B, G, losses.data_ptr(),
+                                           best.data_ptr(), worst.data_ptr(), self._stream()))
+        return {"losses": losses, "best": best, "worst": worst}
+
+    # ------------------------------------------------------------------ the hot loop
+    def reverse_diffusion(self, data: torch.Tensor, n_generated_samples: int, *, noise: Optional[torch.Tensor] = None,
+                          seed: int = 0, first_window: int = 0, want_losses: bool = False, want_worst: bool = False,
+                          want_samples: bool = False, tile_windows: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """The body of MoCoDAD.forward (mocodad.py:129-184) for a batch ``data`` [B,2,seg_len,V].
+
+        ``noise``: None -> in-kernel Philox keyed by (seed, first_window + b, g, slot, element); or the
+        pre-drawn tensor [G, max(N-1,1), B, 2, T, V] in the reference's draw order (slot 0 = x_T).
+        Returns a dict with 'best' [B] and, on request, 'losses' [G,B], 'worst' [B], 'x0' [G,B,2,T,V].
+        """
+        B, G = data.shape[0], int(n_generated_samples)
+        self._chk(data, (B, N_COORDS, self.seg_len, N_JOINTS), "data")
+        if noise is not None:
+            self._chk(noise, (G, max(self.N - 1, 1), B, N_COORDS, self.T, N_JOINTS), "noise")
+        out = {"best": self._new(B)}
+        if want_losses:
+            out["losses"] = self._new(G, B)
+        if want_worst:
+            out["worst"] = self._new(B)
+        if want_samples:
+            out["x0"] = self._new(G, B, N_COORDS, self.T, N_JOINTS)
+        if B == 0:
+            return out
+        nv = G * B
+        tile = min(nv, int(tile_windows) if tile_windows else 16 * self.tile_unit)
+        ws = self._workspace(self.workspace_bytes(tile) + 4 * (B * self.E + nv) + 1024)
+        with torch.cuda.device(self.device):
+            check(self.lib.mcd_reverse_diffusion(
+                self._h, data.data_ptr(), B, G, _ptr(noise), int(seed), int(first_window), _ptr(out.get("losses")),
+                out["best"].data_ptr(), _ptr(out.get("worst")), _ptr(out.get("x0")), ws.data_ptr(), ws.numel(),
+                self._stream()))
+        return out
+
+    def score_windows_host(self, data: torch.Tensor, n_generated_samples: int, *, seed: int = 0,
+                           first_window: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """HOST in, HOST out: ``data`` is a CPU float32 tensor [B,2,seg_len,V] (pinned for speed); the
+        call copies it to the device, runs the loop and copies the [B] 'best' scores back."""
+        if data.device.type != "cpu" or data.dtype != torch.float32 or not data.is_contiguous():
+            raise ValueError("score_windows_host: need a contiguous float32 CPU tensor")
+        B = data.shape[0]
+        if tuple(data.shape) != (B, N_COORDS, self.seg_len, N_JOINTS):
+            raise ValueError(f"score_windows_host: bad shape {tuple(data.shape)}")
+        if out is None:
+            out = torch.empty(B, dtype=torch.float32)
+        check(self.lib.mcd_score_windows_host(self._h, data.data_ptr(), B, int(n_generated_samples), int(seed),
+                                              int(first_window), out.data_ptr()))
+        return out
+
+    # ------------------------------------------------------------------ host-side tables
+    def schedule(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        return schedule(self.N)
+
+    # ------------------------------------------------------------------ measurement
+    def launch_count(self) -> int:
+        return int(self.lib.mcd_launch_count(self._h))
+
+    def profile_enable(self, on: bool = True) -> None:
+        with torch.cuda.device(self.device):
+            check(self.lib.mcd_profile_enable(self._h, int(on)))
+
+    def profile_read(self) -> Dict[str, Dict[str, float]]:
+        n = self.lib.mcd_profile_slots()
+        ms, cnt, win = (C.c_double * n)(), (C.c_int64 * n)(), (C.c_int64 * n)()
+        with torch.cuda.device(self.device):
+            check(self.lib.mcd_profile_read(self._h, ms, cnt, win))
+        res = {}
+        for i in range(n):
+            b, f = C.c_double(), C.c_double()
+            check(self.lib.mcd_profile_slot_cost(self._h, i, C.byref(b), C.byref(f)))
+            res[self.lib.mcd_profile_slot_name(i).decode()] = {
+                "ms": ms[i], "launches": int(cnt[i]), "windows": int(win[i]),
+                "bytes_per_window": b.value, "flops_per_window": f.value}
+        return res
+
+
+def schedule(noise_steps: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(beta, alpha, alpha_hat) fp32 CPU tensors -- models/mocodad.py:799-808 via the library's host function."""
+    lib = _lib.load()
+    arrs = [np.empty(noise_steps, dtype=np.float32) for _ in range(3)]
+    check(lib.mcd_schedule(noise_steps, *[a.ctypes.data_as(_lib.c_float_p) for a in arrs]))
+    return tuple(torch.from_numpy(a) for a in arrs)
+
+
+def pos_encoding(t: int, channels: int) -> torch.Tensor:
+    lib = _lib.load()
+    a = np.empty(channels, dtype=np.float32)
+    check(lib.mcd_pos_encoding(int(t), channels, a.ctypes.data_as(_lib.c_float_p)))
+    return torch.from_numpy(a)
+
+
+def ddpm_coefficients(noise_steps: int, t: int) -> Tuple[float, float, float]:
+    lib = _lib.load()
+    c = [C.c_float() for _ in range(3)]
+    check(lib.mcd_ddpm_coefficients(noise_steps, int(t), *[C.byref(x) for x in c]))
+    return tuple(x.value for x in c)
+
+
+def probe_fp32_tflops(device: int = 0) -> float:
+    lib = _lib.load()
+    v = C.c_double()
+    check(lib.mcd_probe_fp32_tflops(int(device), C.byref(v)))
+    return v.value

@@ -1,0 +1,427 @@
+"""Host-side mirror of the reference's ``MoCoDAD`` LightningModule for the inference/scoring path.
+
+Same constructor (``MoCoDAD(args)`` from the YAML ``Namespace``), same ``forward`` /
+``test_step`` / ``validation_step`` / epoch hooks, same ``state_dict`` names (Lightning checkpoints
+load unchanged) as models/mocodad.py:22-334 -- but ``forward`` hands the whole reverse-diffusion
+loop (mocodad.py:129-184) to the sm_100a CUDA library through the C ABI.  There is no PyTorch
+implementation of the arithmetic in this package: on a machine without the library or without a
+CUDA device ``forward`` raises.
+
+Scope: conditioning strategies 'inject' and 'no_condition' (every shipped
+config uses 'inject'); 'concat' / 'inbetween_imp' / 'random_imp' raise NotImplementedError, as do
+the training entry points.  Optional new knobs are read with ``getattr(args, ..., default)``:
+  b200_rng    'philox' (default; in-kernel counter-based noise keyed by seed / window / sample /
+              step) or 'torch' (noise drawn with torch.randn in the reference's call order
+              mocodad.py:162,176 and injected, so a seeded run reproduces the reference's draws)
+  seed        Philox key (the YAML key the reference carries but never uses at eval time)
+"""
+from __future__ import annotations
+
+import argparse
+import os
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import engine as _engine
+from .params import state_dict_spec
+
+try:  # the reference's orchestration layer, when installed
+    import pytorch_lightning as _pl
+    _Base = _pl.LightningModule
+except Exception:  # pragma: no cover - Lightning is absent in the build container
+    class _Base(nn.Module):
+        """The slice of LightningModule the scoring path touches (mocodad.py:41-43,230-321)."""
+
+        def __init__(self):
+            super().__init__()
+            self.hparams = argparse.Namespace()
+            self._logged: Dict[str, float] = {}
+
+        @property
+        def device(self) -> torch.device:
+            for p in self.parameters():
+                return p.device
+            return torch.device("cpu")
+
+        def save_hyperparameters(self, args=None, *a, **k) -> None:
+            if args is not None:
+                self.hparams = args
+
+        def log(self, name, value, *a, **k) -> None:
+            self._logged[name] = float(value)
+
+        def on_test_epoch_start(self) -> None:
+            pass
+
+        def on_validation_epoch_start(self) -> None:
+            pass
+
+
+class _ParamNode(nn.Module):
+    """Plain container: gives parameters/buffers the dotted names of the reference modules."""
+
+
+def _build_param_tree(root: nn.Module, spec) -> None:
+    for name, shape in spec.items():
+        node = root
+        parts = name.split(".")
+        for part in parts[:-1]:
+            if part not in node._modules:
+                node.add_module(part, _ParamNode())
+            node = node._modules[part]
+        leaf = parts[-1]
+        if leaf == "num_batches_tracked":
+            node.register_buffer(leaf, torch.tensor(0, dtype=torch.long))
+        elif leaf in ("running_mean", "running_var"):
+            node.register_buffer(leaf, torch.zeros(shape) if leaf == "running_mean" else torch.ones(shape))
+        else:
+            node.register_parameter(leaf, nn.Parameter(_init_like_reference(name, shape, spec), requires_grad=False))
+
+
+def _init_like_reference(name: str, shape, spec) -> torch.Tensor:
+    """Fresh-module values with the reference's init distributions (stsgcn.py:135-140 for A/T;
+    torch defaults for conv / linear / BatchNorm / PReLU).  Checkpoints overwrite all of them."""
+    leaf = name.rsplit(".", 1)[-1]
+    if leaf in ("A", "T"):
+        bound = 1.0 / float(shape[1]) ** 0.5
+        return torch.empty(shape).uniform_(-bound, bound)
+    if name.endswith("prelu.weight"):
+        return torch.full(shape, 0.25)
+    if ".tcn.1." in name or ".residual.1." in name or ".block.1." in name:  # BatchNorm affine
+        return torch.ones(shape) if leaf == "weight" else torch.zeros(shape)
+    wshape = spec[name[: -len(leaf)] + "weight"]
+    fan_in = 1
+    for d in wshape[1:]:
+        fan_in *= d
+    bound = 1.0 / float(fan_in) ** 0.5
+    return torch.empty(shape).uniform_(-bound, bound)
+
+
+class MoCoDAD(_Base):
+    """Drop-in for ``models.mocodad.MoCoDAD`` on the test / validation / predict path."""
+
+    losses = ("l1", "smooth_l1", "mse")  # mocodad.py:24
+    conditioning_strategies = {'cat': 'concat', 'concat': 'concat',  # mocodad.py:25-29
+                               'add2layers': 'inject', 'inject': 'inject',
+                               'inbetween_imp': 'inbetween_imp', 'interleave': 'inbetween_imp',
+                               'random_indices': 'random_imp', 'random_imp': 'random_imp',
+                               'no_condition': 'no_condition', 'none': 'no_condition'}
+
+    def __init__(self, args: argparse.Namespace) -> None:
+        super().__init__()
+        self.save_hyperparameters(args)
+        # Data parameters (mocodad.py:46-48)
+        self.n_frames = args.seg_len
+        self.num_coords = args.num_coords
+        self.n_joints = self._infer_number_of_joint(args)
+        # Model parameters (mocodad.py:51-62)
+        self.embedding_dim = args.embedding_dim
+        self.dropout = args.dropout
+        self.conditioning_strategy = self.conditioning_strategies[args.conditioning_strategy]
+        self.conditioning_indices = args.conditioning_indices
+        self.n_frames_condition, self.n_frames_corrupt, self.input_n_frames = self._set_conditioning_strategy()
+        self.conditioning_architecture = args.conditioning_architecture if self.conditioning_strategy == 'inject' else None
+        self.cond_h_dim = args.h_dim
+        self.cond_latent_dim = args.latent_dim
+        self.cond_channels = args.channels
+        self.cond_dropout = args.dropout
+        # Training and inference parameters (mocodad.py:65-81)
+        self.learning_rate = args.opt_lr
+        if args.loss_fn not in self.losses:
+            raise KeyError(args.loss_fn)
+        self.loss_fn_name = args.loss_fn
+        self.rec_weight = args.rec_weight
+        self.noise_steps = args.noise_steps
+        self.aggregation_strategy = args.aggregation_strategy
+        self.n_generated_samples = args.n_generated_samples
+        self.model_return_value = args.model_return_value
+        self.gt_path = args.gt_path
+        self.split = args.split
+        self.use_hr = args.use_hr
+        self.ckpt_dir = args.ckpt_dir
+        self.save_tensors = args.save_tensors
+        self.num_transforms = args.num_transform
+        self.anomaly_score_pad_size = args.pad_size
+        self.anomaly_score_filter_kernel_size = args.filter_kernel_size
+        self.anomaly_score_frames_shift = args.frames_shift
+        self.dataset_name = args.dataset_choice
+        # knobs new to this implementation (optional)
+        self.rng_mode = getattr(args, "b200_rng", "philox")
+        if self.rng_mode not in ("philox", "torch"):
+            raise ValueError(f"b200_rng must be 'philox' or 'torch', got {self.rng_mode!r}")
+        self.seed = int(getattr(args, "seed", 999) or 0)
+        self._window_cursor = 0  # global index of the next window this module scores (Philox counter)
+
+        self._set_diffusion_variables()
+        self.build_model()
+
+    # ------------------------------------------------------------------ construction
+    def build_model(self) -> None:
+        """mocodad.py:90-126 -- here: the parameter tree (reference names) + a lazily built engine."""
+        if self.conditioning_strategy == 'inject':
+            if self.conditioning_architecture not in ('AE', 'E'):
+                raise NotImplementedError(f'Conditioning architecture {self.conditioning_architecture} not implemented.')
+            if self.cond_latent_dim != self.embedding_dim:
+                raise ValueError("latent_dim must equal embedding_dim: the condition embedding is added to the "
+                                 "time embedding (stsae_unet.py:425-426)")
+        if self.n_joints != 17:
+            raise NotImplementedError(f"{self.n_joints} joints: the denoiser's joint pyramid is fixed at 17/12/10 "
+                                      "(stsae_unet.py:11); headless / kp18 layouts fail in the reference too")
+        spec = state_dict_spec(T=self.input_n_frames, T_cond=self.n_frames_condition, num_coords=self.num_coords,
+                               embedding_dim=self.embedding_dim, h_dim=self.cond_h_dim, latent_dim=self.cond_latent_dim,
+                               channels=self.cond_channels, conditioning_architecture=self.conditioning_architecture,
+                               n_joints=self.n_joints)
+        self._spec = spec
+        _build_param_tree(self, spec)
+        self._engine: Optional[_engine.ScoringEngine] = None
+        self._engine_key = None
+
+    def _set_conditioning_strategy(self) -> Tuple[int, int, int]:
+        """mocodad.py:753-796 restricted to the strategies this path implements."""
+        input_n_frames = self.n_frames
+        if self.conditioning_strategy == 'no_condition':
+            n_frames_cond = 0
+        elif self.conditioning_strategy == 'inject':
+            if isinstance(self.conditioning_indices, int):
+                n_frames_cond = self.n_frames // self.conditioning_indices
+                self._cond_first = True
+            else:
+                idx = list(self.conditioning_indices)
+                assert idx == list(range(min(idx), max(idx) + 1)), \
+                    'Conditioning indices must be a list of consecutive integers'
+                assert (min(idx) == 0) or (max(idx) == (self.n_frames - 1)), \
+                    'Conditioning indices must start from 0 or end at the last frame'
+                n_frames_cond = len(idx)
+                self._cond_first = min(idx) == 0
+            input_n_frames = self.n_frames - n_frames_cond
+        elif self.conditioning_strategy in ('concat', 'inbetween_imp', 'random_imp'):
+            raise NotImplementedError(
+                f"conditioning strategy '{self.conditioning_strategy}' is outside the B200 scoring path "
+                "(no shipped config uses it; SURVEY.md section 2)")
+        else:
+            raise NotImplementedError(f'Conditioning strategy {self.conditioning_strategy} not implemented')
+        if not hasattr(self, "_cond_first"):
+            self._cond_first = True
+        return n_frames_cond, self.n_frames - n_frames_cond, input_n_frames
+
+    def _set_diffusion_variables(self) -> None:
+        """mocodad.py:799-808; the table comes from the library's host function (bit-identical)."""
+        self._beta_, self._alpha_, self._alpha_hat_ = _engine.schedule(self.noise_steps)
+
+    def _infer_number_of_joint(self, args: argparse.Namespace) -> int:
+        """mocodad.py:563-580"""
+        if args.headless:
+            return 14
+        if args.kp18_format:
+            return 18
+        return 17
+
+    # ------------------------------------------------------------------ engine
+    def _weights_key(self):
+        dev = self.device
+        ver = 0
+        for t in list(self.parameters()) + list(self.buffers()):
+            ver += t._version
+        first = next(self.parameters())
+        return (str(dev), ver, first.data_ptr())
+
+    def engine(self) -> _engine.ScoringEngine:
+        """The CUDA engine for the module's current device and weights (re-packed when they change)."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("MoCoDAD (B200) computes only on a CUDA device: move the module with .to('cuda'); "
+                               "there is no CPU fallback")
+        key = self._weights_key()
+        if self._engine is None or self._engine.device != torch.device(dev.type, dev.index if dev.index is not None else torch.cuda.current_device()):
+            self._engine = _engine.ScoringEngine(
+                seg_len=self.n_frames, n_frames_cond=self.n_frames_condition, cond_first=self._cond_first,
+                noise_steps=self.noise_steps, loss_fn=self.loss_fn_name, embedding_dim=self.embedding_dim,
+                h_dim=self.cond_h_dim, channels=self.cond_channels, device=dev, n_joints=self.n_joints,
+                num_coords=self.num_coords)
+            self._engine_key = None
+        if key != self._engine_key:
+            self._engine.load_state_dict(self.state_dict())
+            self._engine_key = key
+        return self._engine
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, input_data: List[torch.Tensor], aggr_strategy: str = None, return_: str = None) -> List[torch.Tensor]:
+        """mocodad.py:129-184.  ``input_data`` = [data [B,C,seg_len,V], transformation_idx, metadata,
+        actual_frames]; returns [loss and/or selected poses] + [data, transformation_idx, metadata, frames]."""
+        tensor_data, meta_out = self._unpack_data(input_data)
+        eng = self.engine()
+        data = tensor_data.to(torch.float32).contiguous()
+        B = data.shape[0]
+        G = self.n_generated_samples
+        aggr = self.aggregation_strategy if aggr_strategy is None else aggr_strategy
+        if return_ is None:
+            if self.model_return_value is None:
+                raise ValueError('Either return_ or self.model_return_value must be set')
+            return_ = self.model_return_value
+        need_pose = return_ in ('pose', 'all')
+
+        noise = None
+        if self.rng_mode == "torch":  # the reference's draw order: per sample x_T then z_{N-1}..z_2
+            slots = max(self.noise_steps - 1, 1)
+            noise = torch.empty(G, slots, B, self.num_coords, self.input_n_frames, self.n_joints, device=data.device)
+            for g in range(G):
+                for k in range(self.noise_steps - 1 if self.noise_steps > 1 else 1):
+                    noise[g, k] = torch.randn(B, self.num_coords, self.input_n_frames, self.n_joints, device=data.device)
+        first_window = self._window_cursor
+        self._window_cursor += B
+
+        if aggr == 'random':  # mocodad.py:479-480 returns a bare sample
+            res = eng.reverse_diffusion(data, G, noise=noise, seed=self.seed, first_window=first_window, want_samples=True)
+            return res["x0"][np.random.randint(G)]
+        simple = aggr in ('best', 'worst') and not need_pose
+        res = eng.reverse_diffusion(data, G, noise=noise, seed=self.seed, first_window=first_window,
+                                    want_losses=not simple, want_worst=(aggr == 'worst'),
+                                    want_samples=need_pose or aggr in ('all', 'mean_pose', 'median_pose'))
+        selected_x, loss = self._aggregate(eng, res, data, aggr, need_pose)
+        return self._pack_out_data(selected_x, loss, [tensor_data] + meta_out, return_=return_)
+
+    def _aggregate(self, eng, res, data, aggr: str, need_pose: bool):
+        """mocodad.py:454-520 on the per-sample losses [G,B] (and samples) the library produced."""
+        if aggr in ('best', 'worst'):
+            loss = res['best'] if aggr == 'best' else res['worst']
+            sel = None
+            if need_pose:
+                losses = res['losses']
+                idx = torch.argmin(losses, dim=0) if aggr == 'best' else torch.argmax(losses, dim=0)
+                sel = res['x0'][idx, torch.arange(losses.shape[1], device=losses.device)]
+            return sel, loss
+        losses = res['losses']
+        if aggr == 'all':
+            return res['x0'].permute(1, 0, 2, 3, 4), losses.permute(1, 0)
+        if aggr == 'mean':
+            return None, torch.mean(losses, dim=0)
+        if aggr == 'median':
+            return None, torch.median(losses, dim=0)[0]
+        if aggr in ('mean_pose', 'median_pose'):
+            sel = torch.mean(res['x0'], dim=0) if aggr == 'mean_pose' else torch.median(res['x0'], dim=0)[0]
+            sel = sel.contiguous()
+            return sel, eng.window_loss(sel, data, 1)['best']
+        if 'quantile' in aggr:
+            q = float(aggr.split(':')[-1])
+            return None, torch.quantile(losses, q, dim=0)
+        raise ValueError(f'Unknown aggregation strategy {aggr}')
+
+    def _pack_out_data(self, selected_x, loss_of_selected_x, additional_out, return_: str):
+        """mocodad.py:606-636"""
+        if return_ == 'pose':
+            out = [selected_x]
+        elif return_ == 'loss':
+            out = [loss_of_selected_x]
+        elif return_ == 'all':
+            out = [loss_of_selected_x, selected_x]
+        else:
+            raise ValueError(f"unknown return_ {return_!r}")
+        return out + additional_out
+
+    def _unpack_data(self, x) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+        """mocodad.py:843-858"""
+        return x[0].to(self.device), [x[1], x[2], x[3]]
+
+    # ------------------------------------------------------------------ Lightning surface
+    def test_step(self, batch: List[torch.Tensor], batch_idx: int) -> None:
+        self._test_output_list.append(self.forward(batch))
+
+    def on_test_epoch_start(self) -> None:
+        super().on_test_epoch_start()
+        self._test_output_list = []
+        self._window_cursor = 0
+
+    def on_test_epoch_end(self) -> float:
+        auc = self._epoch_end(self._test_output_list)
+        del self._test_output_list
+        self.log('AUC', auc)
+        return auc
+
+    def validation_step(self, batch: List[torch.Tensor], batch_idx: int) -> None:
+        self._validation_output_list.append(self.forward(batch))
+
+    def on_validation_epoch_start(self) -> None:
+        super().on_validation_epoch_start()
+        self._validation_output_list = []
+        self._window_cursor = 0
+
+    def on_validation_epoch_end(self) -> float:
+        auc = self._epoch_end(self._validation_output_list)
+        del self._validation_output_list
+        self.log('AUC', auc, sync_dist=True)
+        return auc
+
+    def predict_step(self, batch, batch_idx: int = 0, dataloader_idx: int = 0):
+        return self.forward(batch)
+
+    def training_step(self, batch, batch_idx):
+        raise NotImplementedError("training is outside the B200 scoring path (SURVEY.md section 8 f4); "
+                                  "train with the reference and load the checkpoint here")
+
+    def configure_optimizers(self):
+        raise NotImplementedError("training is outside the B200 scoring path")
+
+    def _epoch_end(self, outputs) -> float:
+        out, gt_data, trans, meta, frames = _processing_data(outputs)
+        if self.save_tensors:
+            self._save_tensors({'prediction': out, 'gt_data': gt_data, 'trans': trans, 'metadata': meta, 'frames': frames},
+                               split_name=self.split, aggr_strategy=self.aggregation_strategy, n_gen=self.n_generated_samples)
+        return self.post_processing(out, gt_data, trans, meta, frames)
+
+    def post_processing(self, out, gt_data, trans, meta, frames) -> float:
+        """Score assembly -> AUC (mocodad.py:337-430).  Host-side numpy/scipy/sklearn code that is
+        consumed unchanged from the reference tree: this method borrows the
+        reference's own function, so it needs the reference repo on sys.path."""
+        try:
+            from models.mocodad import MoCoDAD as _Ref  # the reference checkout
+        except Exception as e:  # pragma: no cover
+            raise RuntimeError("post_processing delegates to the reference's models/mocodad.py (host-side AUC code, "
+                               "out of this path's scope); put the reference checkout on sys.path") from e
+        if _Ref is MoCoDAD:
+            raise RuntimeError("models.mocodad resolves to this class; keep the reference's post_processing importable")
+        return _Ref.post_processing(self, out, gt_data, trans, meta, frames)
+
+    def test_on_saved_tensors(self, split_name: str) -> float:
+        """mocodad.py:433-448"""
+        tensors = self._load_tensors(split_name, self.aggregation_strategy, self.n_generated_samples)
+        auc_score = self.post_processing(tensors['prediction'], tensors['gt_data'], tensors['trans'],
+                                         tensors['metadata'], tensors['frames'])
+        print(f'AUC score: {auc_score:.6f}')
+        return auc_score
+
+    def _load_tensors(self, split_name: str, aggr_strategy: str, n_gen: int) -> Dict[str, torch.Tensor]:
+        """mocodad.py:583-603"""
+        path = os.path.join(self.ckpt_dir, 'saved_tensors_{}_{}_{}'.format(split_name, aggr_strategy, n_gen))
+        return {f.split('.')[0]: torch.load(os.path.join(path, f)) for f in os.listdir(path)}
+
+    def _save_tensors(self, tensors, split_name: str, aggr_strategy: str, n_gen: int) -> None:
+        """mocodad.py:689-705"""
+        path = os.path.join(self.ckpt_dir, 'saved_tensors_{}_{}_{}'.format(split_name, aggr_strategy, n_gen))
+        os.makedirs(path, exist_ok=True)
+        for t_name, tensor in tensors.items():
+            torch.save(tensor, os.path.join(path, t_name + '.pt'))
+
+    # schedule accessors with the reference's names (mocodad.py:861-873)
+    @property
+    def _beta(self) -> torch.Tensor:
+        return self._beta_.to(self.device)
+
+    @property
+    def _alpha(self) -> torch.Tensor:
+        return self._alpha_.to(self.device)
+
+    @property
+    def _alpha_hat(self) -> torch.Tensor:
+        return self._alpha_hat_.to(self.device)
+
+
+def _processing_data(data):
+    """utils/model_utils.py:110-137 -- concatenate the per-batch outputs on the host."""
+    cols = [[], [], [], [], []]
+    for arr in data:
+        for c, t in zip(cols, arr[:5]):
+            c.append(t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t))
+    return tuple(np.concatenate(c, axis=0) for c in cols)

@@ -1,0 +1,71 @@
+"""The host-side mirror of models.mocodad.MoCoDAD: constructor surface, state_dict layout, error
+behaviour.  CPU only -- forward needs the GPU and says so."""
+import argparse
+
+import pytest
+import torch
+
+from mocodad_b200 import MoCoDAD, state_dict_spec
+from oracle import synth
+
+BASE = dict(seg_len=6, num_coords=2, headless=False, kp18_format=False, embedding_dim=16, dropout=0.0,
+            conditioning_strategy="inject", conditioning_indices=[0, 1, 2], conditioning_architecture="AE",
+            h_dim=32, latent_dim=16, channels=[32, 16, 32], opt_lr=1e-4, loss_fn="smooth_l1", rec_weight=0.01,
+            noise_steps=10, aggregation_strategy="best", n_generated_samples=50, model_return_value="loss",
+            gt_path="", split="test", use_hr=False, ckpt_dir="", save_tensors=False, num_transform=5,
+            pad_size=12, filter_kernel_size=30, frames_shift=6, dataset_choice="HR-Avenue", seed=999)
+
+
+def make(**kw):
+    cfg = dict(BASE)
+    cfg.update(kw)
+    return MoCoDAD(argparse.Namespace(**cfg))
+
+
+def test_state_dict_layout_matches_reference_checkpoint():
+    m = make()
+    spec = synth.state_dict_spec(T=3, T_cond=3)  # asserted equal to the real module by oracle/make_golden.py
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(spec.keys())
+    assert all(tuple(sd[k].shape) == tuple(spec[k]) for k in spec)
+    assert len(sd) == 335
+    assert sum(v.numel() for k, v in sd.items() if v.dtype.is_floating_point and "running" not in k) == 142294
+    assert dict(state_dict_spec(T=3)) == dict(spec)
+    m.load_state_dict(synth.synth_state_dict(spec, seed=0), strict=True)
+    assert (m.n_frames_condition, m.n_frames_corrupt, m.input_n_frames) == (3, 3, 3)
+
+
+def test_variants_of_the_constructor():
+    m = make(seg_len=27)
+    assert m.input_n_frames == 24 and len(m.state_dict()) == 335
+    m = make(conditioning_indices=2)  # integer form: first seg_len // 2 frames condition
+    assert m.n_frames_condition == 3
+    m = make(conditioning_indices=[3, 4, 5])
+    assert m._cond_first is False
+    m = make(conditioning_strategy="no_condition", seg_len=3)
+    assert m.n_frames_condition == 0 and not any(k.startswith("condition_encoder") for k in m.state_dict())
+    m = make(conditioning_architecture="E")
+    assert not any("decoder" in k for k in m.state_dict())
+    assert torch.equal(m._alpha_, 1 - m._beta_)
+
+
+def test_out_of_scope_configurations_raise_like_the_reference():
+    with pytest.raises(NotImplementedError):
+        make(conditioning_strategy="concat")
+    with pytest.raises(NotImplementedError):
+        make(conditioning_architecture="E_unet")
+    with pytest.raises(KeyError):
+        make(conditioning_strategy="bogus")
+    with pytest.raises(AssertionError):
+        make(conditioning_indices=[1, 2, 3])
+    with pytest.raises(NotImplementedError):
+        make().training_step(None, 0)
+
+
+def test_forward_refuses_to_run_without_cuda():
+    m = make()
+    batch = synth.synth_batch(4, 6)
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.forward(batch)
