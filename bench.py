@@ -111,7 +111,8 @@ class ClockSampler:
 def cpu_reference_rate(a, n_windows: int, n_samples: int, steps: int, warmup: int):
     """Times oracle/ref_port.py (the reference's PyTorch operators, CPU) on a bounded sample of the
     workload; returns (equivalent windows/s at the workload's n_generated_samples, seconds/step)."""
-    from oracle import ref_port, synth
+    from mocodad_b200 import synthetic as synth
+    from oracle import ref_port
     T = a.seg_len - 3
     torch.set_num_threads(os.cpu_count() or 1)
     sd = synth.synth_state_dict(synth.state_dict_spec(T=T, T_cond=3), seed=0)
@@ -155,7 +156,7 @@ def run_b200(a):
     import torch.distributed as dist
     from mocodad_b200 import ScoringEngine
     from mocodad_b200.engine import probe_fp32_tflops
-    from oracle import synth  # synthetic checkpoint / windows generator (inputs only, nothing is computed with it)
+    from mocodad_b200 import synthetic as synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -133,7 +133,7 @@ def test_module_forward_all_strategies_vs_reference(golden, strategy):
     """Through the reference-facing surface: MoCoDAD(args).forward(batch, aggr_strategy, return_)."""
     import argparse
     from mocodad_b200 import MoCoDAD
-    from tests.test_module import BASE
+    from test_module import BASE
     name = "avenue_T3"
     seg_len, N, G, B = CASES[name]
     g = golden(name)
