@@ -155,7 +155,7 @@ def run_reference(a):
 def run_b200(a):
     import torch.distributed as dist
     from mocodad_b200 import ScoringEngine
-    from mocodad_b200.engine import probe_fp32_tflops
+    from mocodad_b200.engine import probe_fp32_detail
     from mocodad_b200 import synthetic as synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,10 +190,13 @@ def run_b200(a):
     first = rank * B  # this rank's windows in the global index space (weak scaling: B windows per rank)
     step_no = [0]
 
+    from mocodad_b200.sharding import gather_scores
+
     def step_device():
         res = eng.reverse_diffusion(data, G, seed=999, first_window=first + step_no[0] * world * B)
         step_no[0] += 1
-        return res["best"]
+        # N > 1: the path's one exchange -- all-gather of the per-window scores
+        return gather_scores(res["best"], world * B) if world > 1 else res["best"]
 
     def step_host():
         out = eng.score_windows_host(host, G, seed=999, first_window=first + step_no[0] * world * B)
@@ -260,7 +263,8 @@ def run_b200(a):
         hbm_peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
     else:
         hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    fp32_peak = probe_fp32_tflops(local)
+    ffma_peak, ffma2_peak = probe_fp32_detail(local)
+    fp32_peak = max(ffma_peak, ffma2_peak)
     top_sec_per_launch = pv["ms"] * 1e-3 / pv["launches"]
     top_bytes_per_launch = pv["bytes_per_window"] * pv["windows"] / pv["launches"]
     top_flops_per_launch = pv["flops_per_window"] * pv["windows"] / pv["launches"]
@@ -273,7 +277,8 @@ def run_b200(a):
                 "algorithmic_bytes_per_launch": top_bytes_per_launch,
                 "note": "the path is fp32-FMA-bound, not HBM-bound (SURVEY.md 8d): see 'fp32'",
                 "fp32": {"achieved_tflops": round(top_flops_per_launch / top_sec_per_launch / 1e12, 2),
-                         "peak_tflops": round(fp32_peak, 2), "peak_source": "mcd_probe_fp32_tflops (FFMA loop, this GPU)",
+                         "peak_tflops": round(fp32_peak, 2), "peak_source": "mcd_probe_fp32_detail: max of FFMA / FFMA2 register loops on this GPU",
+                         "probe_ffma_tflops": round(ffma_peak, 2), "probe_ffma2_tflops": round(ffma2_peak, 2),
                          "frac": round(top_flops_per_launch / top_sec_per_launch / 1e12 / fp32_peak, 4),
                          "whole_step_tflops": round(B * G * (N - 1) * unet_flops / (ms * 1e-3) / 1e12, 2)}}
 

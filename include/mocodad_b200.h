@@ -182,6 +182,8 @@ MCD_API int mcd_profile_slot_cost(const mcd_model* m, int slot, double* bytes_pe
 /* fp32 FMA throughput of the device (TFLOP/s) from a register-resident FMA loop; the fp32
  * roofline denominator bench.py reports next to the HBM one (MEASURED_PEAKS.json has none). */
 MCD_API int mcd_probe_fp32_tflops(int32_t device, double* tflops);
+/* The two instruction forms separately: scalar FFMA and packed FFMA2 (mcd_probe_fp32_tflops = max). */
+MCD_API int mcd_probe_fp32_detail(int32_t device, double* ffma_tflops, double* ffma2_tflops);
 
 #ifdef __cplusplus
 }

@@ -67,6 +67,7 @@ SIGNATURES = {
     "mcd_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mcd_profile_slot_cost": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mcd_probe_fp32_tflops": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
+    "mcd_probe_fp32_detail": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
 

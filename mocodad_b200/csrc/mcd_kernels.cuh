@@ -40,6 +40,9 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// Blackwell packed fp32 FMA (SASS FFMA2): two lanes per issue slot, same fp32 rounding as two fmaf.
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) { return __ffma2_rn(a, b, c); }
+
 __device__ __forceinline__ float f4get(const float4& v, int i) {
   return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
 }
@@ -126,7 +129,7 @@ struct BlockCfg {
   static constexpr int TW = VP / NWT;
   static_assert(TP4 % TQ == 0 && VP % (2 * NWT) == 0, "tile shapes");
   static_assert(CINP % KC == 0 && COUT % TCO == 0 && kThreads % NCG == 0, "channel tiling");
-  static_assert(RESCONV || (TCO <= KC && KC % TCO == 0), "identity residual needs the co-tile inside one chunk");
+  static_assert(TCO % 2 == 0 && (TCO % 4 == 0 || NCG == 1), "column tile: float4 groups, or the 2-channel output block");
   // shared memory carve-up (floats)
   static constexpr int SM_A = 0;
   static constexpr int SM_TM = SM_A + T * V * VP;
@@ -205,11 +208,12 @@ __global__ void __launch_bounds__(kThreads, 1) stgcn_block_kernel(const BlockWei
 
   // conv register tile of this thread
   const int cg = tid % NCG, pg = tid / NCG;
-  float acc[TPR][TCO];
+  constexpr int TCO2 = TCO / 2;
+  float2 acc[TPR][TCO2];
 #pragma unroll
   for (int i = 0; i < TPR; ++i)
 #pragma unroll
-    for (int j = 0; j < TCO; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TCO2; ++j) acc[i][j] = make_float2(0.f, 0.f);
 
   // flattened (tile, chunk) pipeline: the next pair streams in while this one is computed
   const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
@@ -251,26 +255,26 @@ __global__ void __launch_bounds__(kThreads, 1) stgcn_block_kernel(const BlockWei
       const int col = (task / C4) % (NW * V);  // (window-in-tile, joint)
       const int qt = task / (C4 * NW * V);
       const int wl = col / V, v = col - wl * V;
-      float a[4][TQ];
+      float2 a[2][TQ];  // [channel pair][output frame]
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int q = 0; q < TQ; ++q) a[c][q] = 0.f;
+        for (int q = 0; q < TQ; ++q) a[c][q] = make_float2(0.f, 0.f);
       const float* xp = sXc + (wl * P + v) * CP + c4 * 4;
       const float* tp = sTm + v * TMS + qt * TQ;
 #pragma unroll
       for (int t = 0; t < T; ++t) {
         const float4 x = *reinterpret_cast<const float4*>(xp + t * V * CP);
+        const float2 xlo = make_float2(x.x, x.y), xhi = make_float2(x.z, x.w);
 #pragma unroll
         for (int q4 = 0; q4 < TQ / 4; ++q4) {
           const float4 w = *reinterpret_cast<const float4*>(tp + t * TP4 + q4 * 4);
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) {
             const float wv = f4get(w, qq);
-            a[0][q4 * 4 + qq] = fmaf(x.x, wv, a[0][q4 * 4 + qq]);
-            a[1][q4 * 4 + qq] = fmaf(x.y, wv, a[1][q4 * 4 + qq]);
-            a[2][q4 * 4 + qq] = fmaf(x.z, wv, a[2][q4 * 4 + qq]);
-            a[3][q4 * 4 + qq] = fmaf(x.w, wv, a[3][q4 * 4 + qq]);
+            const float2 ww = make_float2(wv, wv);
+            a[0][q4 * 4 + qq] = ffma2(xlo, ww, a[0][q4 * 4 + qq]);
+            a[1][q4 * 4 + qq] = ffma2(xhi, ww, a[1][q4 * 4 + qq]);
           }
         }
       }
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) stgcn_block_kernel(const BlockWei
 #pragma unroll
       for (int q = 0; q < TQ; ++q) {
         const int qq = qt * TQ + q;
-        if (qq < T) *reinterpret_cast<float4*>(yp + qq * V * CP) = make_float4(a[0][q], a[1][q], a[2][q], a[3][q]);
+        if (qq < T) *reinterpret_cast<float4*>(yp + qq * V * CP) = make_float4(a[0][q].x, a[0][q].y, a[1][q].x, a[1][q].y);
       }
     }
     if constexpr (Cfg::EMB) {
@@ -301,39 +305,39 @@ __global__ void __launch_bounds__(kThreads, 1) stgcn_block_kernel(const BlockWei
       const int wtile = (task / C4) % NWT;
       const int row = task / (C4 * NWT);  // (window-in-tile, frame)
       const int wl = row / T, q = row - wl * T;
-      float a[4][TW];
+      float2 a[2][TW];  // [channel pair][output joint]
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int j = 0; j < TW; ++j) a[c][j] = 0.f;
+        for (int j = 0; j < TW; ++j) a[c][j] = make_float2(0.f, 0.f);
       const float* yp = sY1 + (wl * P + q * V) * CP + c4 * 4;
       const float* ap = sA + q * V * VP + wtile * TW;
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         const float4 y = *reinterpret_cast<const float4*>(yp + v * CP);
+        const float2 ylo = make_float2(y.x, y.y), yhi = make_float2(y.z, y.w);
 #pragma unroll
         for (int j2 = 0; j2 < TW / 2; ++j2) {
           const float2 w = *reinterpret_cast<const float2*>(ap + v * VP + j2 * 2);
-          a[0][j2 * 2] = fmaf(y.x, w.x, a[0][j2 * 2]);
-          a[1][j2 * 2] = fmaf(y.y, w.x, a[1][j2 * 2]);
-          a[2][j2 * 2] = fmaf(y.z, w.x, a[2][j2 * 2]);
-          a[3][j2 * 2] = fmaf(y.w, w.x, a[3][j2 * 2]);
-          a[0][j2 * 2 + 1] = fmaf(y.x, w.y, a[0][j2 * 2 + 1]);
-          a[1][j2 * 2 + 1] = fmaf(y.y, w.y, a[1][j2 * 2 + 1]);
-          a[2][j2 * 2 + 1] = fmaf(y.z, w.y, a[2][j2 * 2 + 1]);
-          a[3][j2 * 2 + 1] = fmaf(y.w, w.y, a[3][j2 * 2 + 1]);
+          const float2 w0 = make_float2(w.x, w.x), w1 = make_float2(w.y, w.y);
+          a[0][j2 * 2] = ffma2(ylo, w0, a[0][j2 * 2]);
+          a[1][j2 * 2] = ffma2(yhi, w0, a[1][j2 * 2]);
+          a[0][j2 * 2 + 1] = ffma2(ylo, w1, a[0][j2 * 2 + 1]);
+          a[1][j2 * 2 + 1] = ffma2(yhi, w1, a[1][j2 * 2 + 1]);
         }
       }
       float* zp = sY2 + (wl * P + q * V) * CP + c4 * 4;
 #pragma unroll
       for (int j = 0; j < TW; ++j) {
         const int w = wtile * TW + j;
-        if (w < V) *reinterpret_cast<float4*>(zp + w * CP) = make_float4(a[0][j], a[1][j], a[2][j], a[3][j]);
+        if (w < V) *reinterpret_cast<float4*>(zp + w * CP) = make_float4(a[0][j].x, a[0][j].y, a[1][j].x, a[1][j].y);
       }
     }
     __syncthreads();
 
     // ---- phase 3: 1x1 conv accumulate  acc[r][co] += Y2[r][k]*W[k][co] (+ X[r][k]*Wr[k][co])
+    // Column ownership is interleaved in groups of 4: thread cg owns columns g*(NCG*4) + cg*4 + [0,4),
+    // so the NCG lanes of a row group read one contiguous 16*NCG-byte span of W[k][:] (no bank conflicts).
     {
       int rows[TPR];
 #pragma unroll
@@ -341,65 +345,59 @@ __global__ void __launch_bounds__(kThreads, 1) stgcn_block_kernel(const BlockWei
         int r = pg + i * NPG;
         rows[i] = r < ROWS ? r : ROWS - 1;  // clamp: padded slots recompute the last row, never stored
       }
+      auto accumulate = [&](const float* __restrict__ sIn, const float* __restrict__ sWt) {
 #pragma unroll
-      for (int k4 = 0; k4 < C4; ++k4) {
-        float4 yv[TPR];
+        for (int k4 = 0; k4 < C4; ++k4) {
+          float4 yv[TPR];
 #pragma unroll
-        for (int i = 0; i < TPR; ++i) yv[i] = *reinterpret_cast<const float4*>(sY2 + rows[i] * CP + k4 * 4);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          float w[TCO];
-          const float* wp = sW + (kc0 + k4 * 4 + kk) * COUT + cg * TCO;
-          if constexpr (TCO % 4 == 0) {
-#pragma unroll
-            for (int j4 = 0; j4 < TCO / 4; ++j4) {
-              const float4 t4 = *reinterpret_cast<const float4*>(wp + j4 * 4);
-              w[j4 * 4] = t4.x; w[j4 * 4 + 1] = t4.y; w[j4 * 4 + 2] = t4.z; w[j4 * 4 + 3] = t4.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < TCO; ++j) w[j] = wp[j];
-          }
-#pragma unroll
-          for (int i = 0; i < TPR; ++i) {
-            const float y = f4get(yv[i], kk);
-#pragma unroll
-            for (int j = 0; j < TCO; ++j) acc[i][j] = fmaf(y, w[j], acc[i][j]);
-          }
-        }
-        if constexpr (RESCONV) {
-#pragma unroll
-          for (int i = 0; i < TPR; ++i) yv[i] = *reinterpret_cast<const float4*>(sXc + rows[i] * CP + k4 * 4);
+          for (int i = 0; i < TPR; ++i) yv[i] = *reinterpret_cast<const float4*>(sIn + rows[i] * CP + k4 * 4);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            float w[TCO];
-            const float* wp = sWr + (kc0 + k4 * 4 + kk) * COUT + cg * TCO;
+            float2 w[TCO2];
+            const float* wp = sWt + (kc0 + k4 * 4 + kk) * COUT;
             if constexpr (TCO % 4 == 0) {
 #pragma unroll
-              for (int j4 = 0; j4 < TCO / 4; ++j4) {
-                const float4 t4 = *reinterpret_cast<const float4*>(wp + j4 * 4);
-                w[j4 * 4] = t4.x; w[j4 * 4 + 1] = t4.y; w[j4 * 4 + 2] = t4.z; w[j4 * 4 + 3] = t4.w;
+              for (int g = 0; g < TCO / 4; ++g) {
+                const float4 t4 = *reinterpret_cast<const float4*>(wp + g * (NCG * 4) + cg * 4);
+                w[g * 2] = make_float2(t4.x, t4.y);
+                w[g * 2 + 1] = make_float2(t4.z, t4.w);
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < TCO; ++j) w[j] = wp[j];
+              for (int j = 0; j < TCO2; ++j) w[j] = *reinterpret_cast<const float2*>(wp + cg * TCO + j * 2);
             }
 #pragma unroll
             for (int i = 0; i < TPR; ++i) {
               const float y = f4get(yv[i], kk);
+              const float2 yy = make_float2(y, y);
 #pragma unroll
-              for (int j = 0; j < TCO; ++j) acc[i][j] = fmaf(y, w[j], acc[i][j]);
+              for (int j = 0; j < TCO2; ++j) acc[i][j] = ffma2(yy, w[j], acc[i][j]);
             }
           }
         }
-      }
-      if constexpr (!RESCONV) {  // identity residual: this thread's co-tile lives in exactly one chunk
-        if ((cg * TCO) / KC == chunk) {
-          const int off = cg * TCO - kc0;
+      };
+      accumulate(sY2, sW);
+      if constexpr (RESCONV) accumulate(sXc, sWr);
+      if constexpr (!RESCONV) {  // identity residual: a 4-column group lies inside exactly one K chunk
 #pragma unroll
-          for (int i = 0; i < TPR; ++i)
+        for (int g = 0; g < (TCO + 3) / 4; ++g) {
+          const int co0 = TCO % 4 == 0 ? g * (NCG * 4) + cg * 4 : cg * TCO;
+          if (co0 / KC == chunk) {
 #pragma unroll
-            for (int j = 0; j < TCO; ++j) acc[i][j] += sXc[rows[i] * CP + off + j];
+            for (int i = 0; i < TPR; ++i) {
+              if constexpr (TCO % 4 == 0) {
+                const float4 xv = *reinterpret_cast<const float4*>(sXc + rows[i] * CP + (co0 - kc0));
+                acc[i][g * 2].x += xv.x; acc[i][g * 2].y += xv.y;
+                acc[i][g * 2 + 1].x += xv.z; acc[i][g * 2 + 1].y += xv.w;
+              } else {
+#pragma unroll
+                for (int j = 0; j < TCO2; ++j) {
+                  acc[i][j].x += sXc[rows[i] * CP + (co0 - kc0) + j * 2];
+                  acc[i][j].y += sXc[rows[i] * CP + (co0 - kc0) + j * 2 + 1];
+                }
+              }
+            }
+          }
         }
       }
 
@@ -412,36 +410,49 @@ __global__ void __launch_bounds__(kThreads, 1) stgcn_block_kernel(const BlockWei
           const int wl = r / P;
           const int64_t w = tile * NW + wl;
           const bool ok = (r < ROWS) && (w < io.n);
-          float o[TCO];
-#pragma unroll
-          for (int j = 0; j < TCO; ++j) {
-            const int co = cg * TCO + j;
-            float v = acc[i][j] + sBias[co];
+          const float* embp = sEmb + (ok ? wl : 0) * COUT;
+          auto finish = [&](float v, int co) {
+            v += sBias[co];
             v = v > 0.f ? v : slope * v;
-            if constexpr (Cfg::EMB) v += sEmb[(ok ? wl : 0) * COUT + co];
-            o[j] = v;
-            acc[i][j] = 0.f;
-          }
-          if (ok) {
-            if constexpr (Cfg::OUTMODE == OUT_CL) {
-              float* dst = io.out + (tile * ROWS + r) * COUT + cg * TCO;
-              if constexpr (TCO % 4 == 0) {
+            if constexpr (Cfg::EMB) v += embp[co];
+            return v;
+          };
+          if constexpr (Cfg::OUTMODE == OUT_CL) {
+            float* dst = io.out + (tile * ROWS + r) * COUT;
+            if constexpr (TCO % 4 == 0) {
 #pragma unroll
-                for (int j4 = 0; j4 < TCO / 4; ++j4)
-                  *reinterpret_cast<float4*>(dst + j4 * 4) = make_float4(o[j4 * 4], o[j4 * 4 + 1], o[j4 * 4 + 2], o[j4 * 4 + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < TCO; ++j) dst[j] = o[j];
+              for (int g = 0; g < TCO / 4; ++g) {
+                const int co0 = g * (NCG * 4) + cg * 4;
+                const float4 o = make_float4(finish(acc[i][g * 2].x, co0), finish(acc[i][g * 2].y, co0 + 1),
+                                             finish(acc[i][g * 2 + 1].x, co0 + 2), finish(acc[i][g * 2 + 1].y, co0 + 3));
+                if (ok) *reinterpret_cast<float4*>(dst + co0) = o;
               }
-            } else {  // OUT_EPS: reference layout [n][COUT][P], plus the U-Net's outer residual +X
-              const int p = r - wl * P;
+            } else {
 #pragma unroll
-              for (int j = 0; j < TCO; ++j) {
-                const int64_t e = (w * COUT + (cg * TCO + j)) * P + p;
-                io.out[e] = io.xres != nullptr ? o[j] + io.xres[e] : o[j];
+              for (int j = 0; j < TCO2; ++j) {
+                const int co0 = cg * TCO + j * 2;
+                const float2 o = make_float2(finish(acc[i][j].x, co0), finish(acc[i][j].y, co0 + 1));
+                if (ok) *reinterpret_cast<float2*>(dst + co0) = o;
+              }
+            }
+          } else {  // OUT_EPS: reference layout [n][COUT][P], plus the U-Net's outer residual +X
+            static_assert(Cfg::OUTMODE == OUT_CL || TCO == 2, "OUT_EPS is the 2-channel output block");
+            const int p = r - wl * P;
+            if (ok) {
+#pragma unroll
+              for (int j = 0; j < TCO2; ++j) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const int co = cg * TCO + j * 2 + h;
+                  const int64_t e = (w * COUT + co) * P + p;
+                  const float o = finish(h == 0 ? acc[i][j].x : acc[i][j].y, co);
+                  io.out[e] = io.xres != nullptr ? o + io.xres[e] : o;
+                }
               }
             }
           }
+#pragma unroll
+          for (int j = 0; j < TCO2; ++j) acc[i][j] = make_float2(0.f, 0.f);
         }
       }
     }

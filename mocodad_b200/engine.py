@@ -281,3 +281,11 @@ def probe_fp32_tflops(device: int = 0) -> float:
     v = C.c_double()
     check(lib.mcd_probe_fp32_tflops(int(device), C.byref(v)))
     return v.value
+
+
+def probe_fp32_detail(device: int = 0) -> Tuple[float, float]:
+    """(scalar FFMA, packed FFMA2) TFLOP/s of the device."""
+    lib = _lib.load()
+    a, b = C.c_double(), C.c_double()
+    check(lib.mcd_probe_fp32_detail(int(device), C.byref(a), C.byref(b)))
+    return a.value, b.value
