@@ -5,11 +5,13 @@
 // No torch, no allocation on the compute path; every failure is reported, nothing falls back.
 #include "../../include/mocodad_b200.h"
 #include "mcd_kernels.cuh"
+#include "mcd_block_tc.cuh"
 
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -100,6 +102,7 @@ struct mcd_model {
   int T = 0, Tc = 0, t0_corrupt = 0, t0_cond = 0, E = 0, N = 0;
   int num_sms = 0;
   bool finalized = false;
+  bool use_tc = true;  // tensor-core channel contraction for the dense blocks (MCD_DISABLE_TC=1 turns it off)
   std::map<std::string, std::vector<float>> tensors;
   float* d_arena = nullptr;
   size_t arena_floats = 0;
@@ -197,20 +200,40 @@ int block_op(int action, const mcd_model* m, int slot, const BlockWeights* w, co
   return launch_block<Cfg>(m, slot, *w, *io, s);
 }
 
+// The dense middle blocks: tensor-core contraction (mcd_block_tc.cuh) unless disabled, else the FMA-pipe kernel.
+template <int T, int V, int CIN, int COUT>
+int dense_block_op(int action, const mcd_model* m, int slot, const BlockWeights* w, const BlockIO* io, cudaStream_t s) {
+  using Tc = TcCfg<T, V, CIN, COUT, nw_for(T, 17)>;
+  static_assert(Tc::SMEM_BYTES <= 227 * 1024, "tensor-core block kernel exceeds the 227 KB shared memory of an sm_100 CTA");
+  if (action == 0) {
+    CUDA_TRY(cudaFuncSetAttribute(stgcn_block_tc_kernel<Tc>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Tc::SMEM_BYTES)));
+    return block_op<T, V, CIN, COUT, true, IN_CL, OUT_CL>(0, m, slot, w, io, s);
+  }
+  if (!m->use_tc || w->Bop == nullptr) return block_op<T, V, CIN, COUT, true, IN_CL, OUT_CL>(1, m, slot, w, io, s);
+  if (io->n <= 0) return MCD_OK;
+  const int64_t ntiles = (io->n + Tc::NW - 1) / Tc::NW;
+  const int grid = int(ntiles < m->num_sms ? ntiles : m->num_sms);
+  {
+    LaunchScope ls(m, slot, io->n, s);
+    stgcn_block_tc_kernel<Tc><<<grid, kTcThreads, Tc::SMEM_BYTES, s>>>(*w, *io);
+  }
+  return check_launch(kSlotNames[slot]);
+}
+
 template <int T>
 int unet_block_op(int action, int idx, const mcd_model* m, const BlockWeights* w, const BlockIO* io, cudaStream_t s) {
   const int slot = SLOT_UNET0 + idx;
   switch (idx) {
     case 0: return block_op<T, 17, 2, 16, true, IN_CF, OUT_CL>(action, m, slot, w, io, s);
     case 1: return block_op<T, 17, 16, 32, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
-    case 2: return block_op<T, 17, 32, 32, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
-    case 3: return block_op<T, 12, 32, 64, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
-    case 4: return block_op<T, 12, 64, 64, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
-    case 5: return block_op<T, 10, 64, 128, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
-    case 6: return block_op<T, 10, 128, 64, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
-    case 7: return block_op<T, 12, 64, 64, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
-    case 8: return block_op<T, 12, 64, 32, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
-    case 9: return block_op<T, 17, 32, 32, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
+    case 2: return dense_block_op<T, 17, 32, 32>(action, m, slot, w, io, s);
+    case 3: return dense_block_op<T, 12, 32, 64>(action, m, slot, w, io, s);
+    case 4: return dense_block_op<T, 12, 64, 64>(action, m, slot, w, io, s);
+    case 5: return dense_block_op<T, 10, 64, 128>(action, m, slot, w, io, s);
+    case 6: return dense_block_op<T, 10, 128, 64>(action, m, slot, w, io, s);
+    case 7: return dense_block_op<T, 12, 64, 64>(action, m, slot, w, io, s);
+    case 8: return dense_block_op<T, 12, 64, 32>(action, m, slot, w, io, s);
+    case 9: return dense_block_op<T, 17, 32, 32>(action, m, slot, w, io, s);
     case 10: return block_op<T, 17, 32, 2, true, IN_CL, OUT_EPS>(action, m, slot, w, io, s);
   }
   return fail(MCD_ERR_INVALID_ARG, "bad U-Net block index %d", idx);
@@ -488,7 +511,7 @@ bool bn_fold(const mcd_model* m, const std::string& p, int C, std::vector<double
   return true;
 }
 
-struct BlockOffsets { size_t A, Tm, W, Wr, bias, WE, bE; };
+struct BlockOffsets { size_t A, Tm, W, Wr, bias, WE, bE, Bop; bool has_bop; };
 
 bool pack_block(const mcd_model* m, Arena* ar, const std::string& p, int cin, int cout, int T, int V, bool emb, int E,
                 PackedBlock* pb, BlockOffsets* off, std::string* missing) {
@@ -546,6 +569,36 @@ bool pack_block(const mcd_model* m, Arena* ar, const std::string& p, int cin, in
     for (int co = 0; co < cout; ++co) ar->h[off->bE + co] = (*bE)[co];
   }
   pb->w.prelu = (*pr)[0];
+  // tensor-core operands (mcd_block_tc.cuh): per 16-channel chunk, parts [W hi | W lo | Wr hi | Wr lo], each
+  // [COUT rows][16 k] fp32 with the 16-byte chunk index XORed by bits 1..2 of the row (UMMA SWIZZLE_64B, K-major).
+  off->has_bop = (cin % 16 == 0) && (cout % 32 == 0);
+  off->Bop = 0;
+  if (off->has_bop) {
+    const int nparts = pb->resconv ? 4 : 2;
+    const size_t wch = size_t(nparts) * cout * 16;
+    off->Bop = ar->alloc(wch * (cin / 16));
+    auto lo_part = [](float w) {
+      uint32_t u;
+      memcpy(&u, &w, 4);
+      u &= 0xFFFFE000u;
+      float hi;
+      memcpy(&hi, &u, 4);
+      return w - hi;
+    };
+    for (int k = 0; k < cin; ++k)
+      for (int co = 0; co < cout; ++co) {
+        const int c = k / 16, kk = k % 16;
+        const size_t pos = size_t(co) * 16 + size_t((((kk >> 2) ^ ((co >> 1) & 3)) << 2) + (kk & 3));
+        const float w = ar->h[off->W + size_t(k) * cout + co];
+        ar->h[off->Bop + c * wch + 0 * size_t(cout) * 16 + pos] = w;
+        ar->h[off->Bop + c * wch + 1 * size_t(cout) * 16 + pos] = lo_part(w);
+        if (pb->resconv) {
+          const float wr = ar->h[off->Wr + size_t(k) * cout + co];
+          ar->h[off->Bop + c * wch + 2 * size_t(cout) * 16 + pos] = wr;
+          ar->h[off->Bop + c * wch + 3 * size_t(cout) * 16 + pos] = lo_part(wr);
+        }
+      }
+  }
   return true;
 }
 
@@ -557,6 +610,7 @@ void bind_block(PackedBlock* pb, const BlockOffsets& off, const float* base) {
   pb->w.bias = base + off.bias;
   pb->w.WEt = pb->emb ? base + off.WE : nullptr;
   pb->w.bE = pb->emb ? base + off.bE : nullptr;
+  pb->w.Bop = off.has_bop ? base + off.Bop : nullptr;
 }
 
 void free_device(mcd_model* m) {
@@ -697,6 +751,8 @@ int mcd_model_create(const mcd_config* cfg, mcd_model** out) {
   if (2 * T * 17 > 65535) return fail(MCD_ERR_UNSUPPORTED, "window too large for the Philox element counter");
   mcd_model* m = new mcd_model();
   m->cfg = *cfg;
+  const char* no_tc = getenv("MCD_DISABLE_TC");
+  m->use_tc = !(no_tc != nullptr && no_tc[0] == '1');
   m->T = T;
   m->Tc = cfg->n_frames_cond;
   m->t0_cond = cfg->cond_first ? 0 : T;

@@ -81,6 +81,8 @@ struct BlockWeights {
   const float* bias;  // [COUT]          folded biases (tcn + residual)
   const float* WEt;   // [E][COUT]       emb_layer.1.weight transposed (nullptr: no embedding)
   const float* bE;    // [COUT]
+  const float* Bop;   // tensor-core path: per 16-channel chunk [W hi | W lo | Wr hi | Wr lo] x [COUT][16], tf32 split,
+                      // pre-arranged in the UMMA K-major SWIZZLE_64B layout (nullptr: block not packed for it)
   float prelu;        // prelu.weight[0]
 };
 
