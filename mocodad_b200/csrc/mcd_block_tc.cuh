@@ -13,7 +13,7 @@
 // accumulator (3xTF32).  tools/tc_probe.cu measures max |error| 3.3e-6 on |values| up to 12.7 at
 // K=64 against fp64 -- the class of an fp32 FMA chain (profiles/r01_tc_probe.log).
 //
-// Structure of one CTA (persistent, one per SM): 8 compute warps + 1 MMA-issuing warp.
+// Structure of one CTA (persistent, one per SM): 8 compute warps + 1 MMA-issuing warp + 4 epilogue warps.
 //   compute warps, per 16-channel chunk of the input:
 //     T-mix  X -> Y1, A-mix Y1 -> Y2 (fp32 FMA pipe, packed FFMA2), writing Y2 and its lo part (and the
 //     lo part of X when the block has a residual convolution) straight into the UMMA K-major
@@ -21,15 +21,19 @@
 //   MMA warp: waits on the named barrier, issues the chunk's tcgen05.mma's (A = activations rows x 16,
 //     B = BN-folded weights Cout x 16, D = TMEM [128 lanes x Cout] per 128-row tile), commits to an
 //     mbarrier; the tensor pipe runs while the compute warps do the T-mix of the next chunk;
-//   after the last chunk the compute warps read the accumulators (tcgen05.ld 32x32b), apply bias,
-//     identity residual, PReLU and the time/condition embedding, and store channel-last.
+//   epilogue warps (one per TMEM lane quarter): when a tile's last commit lands they read the accumulators
+//     (tcgen05.ld 32x32b), apply bias, identity residual, PReLU and the time/condition embedding and store
+//     channel-last, while the compute warps already mix the next tile; TMEM holds two accumulator sets.
 #pragma once
 #include "mcd_kernels.cuh"
 
 namespace mcd {
 
-constexpr int kTcCompute = 256;           // compute threads (8 warps)
-constexpr int kTcThreads = kTcCompute + 32;  // + the MMA-issuing warp
+constexpr int kTcCompute = 256;                     // compute threads (warps 0-7)
+constexpr int kTcMmaWarp = 8;                       // the MMA-issuing warp
+constexpr int kTcEpilogue = 128;                    // epilogue threads (warps 9-12: TMEM lane quarters 1,2,3,0)
+constexpr int kTcThreads = kTcCompute + 32 + kTcEpilogue;
+// named barriers: 1 = operands ready (compute -> MMA warp), 2 = compute-only sync, 3/4 = embedding of an even/odd tile ready (compute -> epilogue)
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -73,6 +77,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
   __trap();
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -85,6 +95,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float4 ldg_nc4(const float* p) {  // read-only global load, streaming
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg4(float* p, const float4 v) {
+  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 // float index of (row r, 4-channel group c4) in a [rows][16] fp32 operand array laid out K-major SWIZZLE_64B
@@ -118,9 +137,10 @@ struct TcCfg {
   static constexpr int NQT = TP4 / TQ;
   static constexpr int NWT = 2;
   static constexpr int TW = VP / NWT;
-  static constexpr int TMEM_COLS = MT * COUT <= 128 ? 128 : (MT * COUT <= 256 ? 256 : 512);
+  static constexpr int ACC_COLS = MT * COUT;  // one accumulator set; TMEM holds two (tile parity)
+  static constexpr int TMEM_COLS = 2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512);
   static_assert(CIN % KC == 0 && COUT % 32 == 0 && COUT <= 256, "tensor-core block: Cin multiple of 16, Cout multiple of 32");
-  static_assert(MT * COUT <= 512, "accumulators exceed TMEM");
+  static_assert(2 * MT * COUT <= 512, "two accumulator sets exceed TMEM");
   static_assert(TP4 % TQ == 0 && VP % (2 * NWT) == 0, "tile shapes");
   // shared memory carve-up, in floats from a 1024-byte aligned base
   static constexpr int ARR = (ROWS * 16 + 127) / 128 * 128;  // operand array stride: multiple of 512 bytes
@@ -135,15 +155,14 @@ struct TcCfg {
   static constexpr int SM_TM = SM_A + T * V * VP;
   static constexpr int SM_BIAS = SM_TM + V * TMS;
   static constexpr int SM_EMB = SM_BIAS + COUT;
-  static constexpr int SM_S = SM_EMB + NW * COUT;
+  static constexpr int SM_S = SM_EMB + 2 * NW * COUT;  // sEmb is double-buffered like the accumulators
   static constexpr int SM_TOTAL = SM_S + NW * kMaxE;
   static_assert((MT * 128 - ROWS) * 16 <= 2 * WCH + T * V * VP, "over-read of the last MMA tile must stay inside the allocation");
   static constexpr size_t SMEM_BYTES = size_t(SM_TOTAL) * sizeof(float) + 1024;  // + alignment slack
 };
 
 template <class Cfg>
-__device__ __forceinline__ void tc_prefetch(const BlockWeights& wt, const BlockIO& io, float* sXbuf, float* sWbuf, int64_t tile,
-                                            int chunk, int tid) {
+__device__ __forceinline__ void tc_prefetch_x(const BlockIO& io, float* sXbuf, int64_t tile, int chunk, int tid) {
   const int64_t row0 = tile * Cfg::ROWS;
   const int64_t nrows = io.n * Cfg::P;
   const float* base = io.in + chunk * Cfg::KC;
@@ -153,6 +172,9 @@ __device__ __forceinline__ void tc_prefetch(const BlockWeights& wt, const BlockI
     const float* src = ok ? base + (row0 + r) * Cfg::CIN + j * 4 : io.in;
     cp_async16(sXbuf + sw_off(r, j), src, ok);
   }
+}
+template <class Cfg>
+__device__ __forceinline__ void tc_prefetch_w(const BlockWeights& wt, float* sWbuf, int chunk, int tid) {
   const float* wsrc = wt.Bop + size_t(chunk) * Cfg::WCH;
   for (int idx = tid; idx < Cfg::WCH / 4; idx += kTcCompute) cp_async16(sWbuf + idx * 4, wsrc + idx * 4, true);
 }
@@ -166,7 +188,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
   constexpr bool RESCONV = Cfg::RESCONV;
 
   extern __shared__ uint8_t smem_raw[];
-  float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align to 1024 B with pointer arithmetic on the shared array (keeps the shared address space: LDS/STS, not generic)
+  float* smem = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   float* sX = smem + Cfg::SM_X;
   float* sY1 = smem + Cfg::SM_Y1;
   float* sXlo = smem + Cfg::SM_XLO;
@@ -178,52 +201,62 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
   float* sBias = smem + Cfg::SM_BIAS;
   float* sEmb = smem + Cfg::SM_EMB;
   float* sS = smem + Cfg::SM_S;
-  __shared__ __align__(8) uint64_t mma_bar;
+  // mbarriers: [0] per-pair MMA commit (operand buffers free), [1],[2] accumulator set full, [3],[4] set drained
+  __shared__ __align__(8) uint64_t bars[5];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (io.n + NW - 1) / NW;
   if (int64_t(blockIdx.x) >= ntiles) return;  // uniform over the CTA
-  const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-  const int64_t npairs = my_tiles * NCHUNK;
+  const int my_tiles = int((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const int npairs = my_tiles * NCHUNK;
 
   // ---- once per CTA ----
-  if (warp == 8) {
+  if (warp == kTcMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
                  "r"(uint32_t(Cfg::TMEM_COLS))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  } else {
+  } else if (warp < kTcMmaWarp) {
     if (tid == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mma_bar)) : "memory");
+      mbar_init(smem_u32(&bars[0]), 1);
+      mbar_init(smem_u32(&bars[1]), 1);
+      mbar_init(smem_u32(&bars[2]), 1);
+      mbar_init(smem_u32(&bars[3]), kTcEpilogue);
+      mbar_init(smem_u32(&bars[4]), kTcEpilogue);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < T * V * VP; i += kTcCompute) sA[i] = wt.A[i];
-    for (int i = tid; i < V * TMS; i += kTcCompute) sTm[i] = wt.Tm[i];
-    for (int i = tid; i < COUT; i += kTcCompute) sBias[i] = wt.bias[i];
+    static_assert((T * V * VP) % 4 == 0 && (V * TMS) % 4 == 0 && COUT % 4 == 0, "16-byte weight copies");
+    for (int i = tid; i < T * V * VP / 4; i += kTcCompute) cp_async16(sA + i * 4, wt.A + i * 4, true);
+    for (int i = tid; i < V * TMS / 4; i += kTcCompute) cp_async16(sTm + i * 4, wt.Tm + i * 4, true);
+    cp_async_commit();  // waited for together with the first activation chunk
+  } else {
+    for (int i = tid - (kTcCompute + 32); i < COUT; i += kTcEpilogue) sBias[i] = wt.bias[i];
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t bar = smem_u32(&mma_bar);
+  const uint32_t bar_mma = smem_u32(&bars[0]);
 
-  if (warp == 8) {
+  if (warp == kTcMmaWarp) {
     // =============================== MMA-issuing warp ===============================
     const uint32_t idesc = umma_idesc_tf32(COUT);
-    for (int64_t it = 0; it < npairs; ++it) {
-      named_bar_sync(1, kTcThreads);  // operands of pair `it` are in shared memory (compute warps fenced + arrived)
+    for (int it = 0; it < npairs; ++it) {
+      const int ti = it / NCHUNK, chunk = it - ti * NCHUNK;
+      const int set = ti & 1;
+      named_bar_sync(1, kTcCompute + 32);  // operands of pair `it` are in shared memory (compute warps fenced + arrived)
+      if (chunk == 0 && ti >= 2) mbar_wait(smem_u32(&bars[3 + set]), uint32_t((ti / 2 - 1) & 1));  // set drained by the epilogue
       tc_fence_after();
       if (lane == 0) {
-        const int chunk = int(it % NCHUNK);
-        const int buf = int(it & 1);
+        const int buf = it & 1;
         const uint32_t aY2 = smem_u32(sY2), aY2lo = smem_u32(sY2lo);
         const uint32_t aX = smem_u32(sX + buf * ARR), aXlo = smem_u32(sXlo);
         const uint32_t bW = smem_u32(sWc + buf * WCH);
         constexpr uint32_t PART = COUT * 64;  // bytes per weight part
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
-          const uint32_t d = tmem + m * COUT;
+          const uint32_t d = tmem + set * Cfg::ACC_COLS + m * COUT;
           const uint32_t moff = m * 128 * 64;
           uint32_t acc = chunk > 0 ? 1u : 0u;
 #pragma unroll
@@ -240,34 +273,92 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
             }
           }
         }
-        umma_commit(bar);
+        umma_commit(bar_mma);
+        if (chunk == NCHUNK - 1) umma_commit(smem_u32(&bars[1 + set]));  // the tile's accumulators are complete
       }
       __syncwarp();
     }
+  } else if (warp > kTcMmaWarp) {
+    // =============================== epilogue warps ===============================
+    // TMEM -> bias, identity residual, PReLU, + emb -> channel-last store            stsgcn.py:109-114
+    const float slope = wt.prelu;
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int64_t tile = blockIdx.x + int64_t(ti) * gridDim.x;
+      const int set = ti & 1;
+      named_bar_sync(3 + set, kTcCompute + kTcEpilogue);  // sEmb[set] of this tile is written
+      mbar_wait(smem_u32(&bars[1 + set]), uint32_t((ti / 2) & 1));
+      tc_fence_after();
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        const int r = m * 128 + q * 32 + lane;
+        const int wl = r / P;
+        const int64_t w = tile * NW + wl;
+        const bool ok = (r < ROWS) && (w < io.n);
+        const float* embp = sEmb + (set * NW + (ok ? wl : 0)) * COUT;
+        const int64_t grow = tile * ROWS + r;
+#pragma unroll 1
+        for (int c0 = 0; c0 < COUT; c0 += 32) {
+          float4 xr[8];
+          if constexpr (!RESCONV) {  // identity residual: issue the loads of this column group before touching TMEM
+            const float* src = io.in + (ok ? grow : 0) * CIN + c0;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) xr[j4] = ldg_nc4(src + j4 * 4);
+          }
+          uint32_t acc[32];
+          tmem_ld32(tmem + (uint32_t(q * 32) << 16) + uint32_t(set * Cfg::ACC_COLS + m * COUT + c0), acc);
+          float* dst = io.out + grow * COUT + c0;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            float o[4];
+            const float4 b4 = *reinterpret_cast<const float4*>(sBias + c0 + j4 * 4);
+            const float4 e4 = *reinterpret_cast<const float4*>(embp + c0 + j4 * 4);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              float v = __uint_as_float(acc[j4 * 4 + jj]) + f4get(b4, jj);
+              if constexpr (!RESCONV) v += f4get(xr[j4], jj);
+              v = v > 0.f ? v : slope * v;
+              o[jj] = v + f4get(e4, jj);
+            }
+            if (ok) stg4(dst + j4 * 4, make_float4(o[0], o[1], o[2], o[3]));
+          }
+        }
+      }
+      tc_fence_before();                   // accumulator reads ordered before the release of the set
+      mbar_arrive(smem_u32(&bars[3 + set]));
+    }
   } else {
     // =============================== compute warps ===============================
-    tc_prefetch<Cfg>(wt, io, sX, sWc, blockIdx.x, 0, tid);
+    tc_prefetch_x<Cfg>(io, sX, blockIdx.x, 0, tid);
+    tc_prefetch_w<Cfg>(wt, sWc, 0, tid);
     cp_async_commit();
-    int64_t waited = 0;  // MMA commits observed so far
+    int waited = 0;  // per-pair MMA commits observed so far
 
-    for (int64_t it = 0; it < npairs; ++it) {
-      const int64_t tile = blockIdx.x + (it / NCHUNK) * gridDim.x;
-      const int chunk = int(it % NCHUNK);
+    for (int it = 0; it < npairs; ++it) {
+      const int ti = it / NCHUNK, chunk = it - ti * NCHUNK;
+      const int64_t tile = blockIdx.x + int64_t(ti) * gridDim.x;
+      const int set = ti & 1;
       float* sXc = sX + (it & 1) * ARR;
+      const bool more = it + 1 < npairs;
+      const int nti = (it + 1) / NCHUNK, nchunk = (it + 1) - nti * NCHUNK;
+      const int64_t ntile = blockIdx.x + int64_t(nti) * gridDim.x;
 
       cp_async_wait_all();
-      named_bar_sync(2, kTcCompute);  // X / W chunk visible; previous pair's mix + epilogue finished everywhere
+      named_bar_sync(2, kTcCompute);  // X / W chunk visible; the previous pair's mix finished everywhere
 
-      // time/condition embedding input  SiLU(pos + cond), stsgcn.py:112-114 (once per tile)
-      if (chunk == 0) {
-        const int E = io.E;
-        for (int i = tid; i < NW * E; i += kTcCompute) {
-          const int wl = i / E, j = i - wl * E;
-          const int64_t w = tile * NW + wl;
-          float v = io.pos[j];
-          if (io.cond != nullptr && w < io.n) v += io.cond[((io.w0 + w) % io.condB) * E + j];
-          sS[wl * kMaxE + j] = v / (1.0f + expf(-v));
-        }
+      // identity blocks: X is not an MMA operand, so its other buffer is free now -- prefetch a whole pair ahead
+      if constexpr (!RESCONV) {
+        if (more) tc_prefetch_x<Cfg>(io, sX + ((it + 1) & 1) * ARR, ntile, nchunk, tid);
+      }
+
+      // time/condition embedding input  pos + cond (stsgcn.py:112-114), once per tile: the global loads are
+      // issued here and consumed after the T-mix, which hides their latency
+      float temb = 0.f;
+      if (chunk == 0 && tid < NW * io.E) {
+        const int wl = tid / io.E, j = tid - wl * io.E;
+        const int64_t w = tile * NW + wl;
+        temb = __ldg(io.pos + j);
+        if (io.cond != nullptr && w < io.n) temb += __ldg(io.cond + ((io.w0 + w) % io.condB) * io.E + j);
       }
 
       // ---- T-mix   Y1[n,(q,v),c] = sum_t X[n,(t,v),c] * Tm[v][t][q]     stsgcn.py:154
@@ -306,14 +397,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
             *reinterpret_cast<float4*>(sY1 + sw_off(r0 + qq * V, c4)) = make_float4(a[0][q].x, a[0][q].y, a[1][q].x, a[1][q].y);
         }
       }
+      if (chunk == 0 && tid < NW * io.E) {
+        const int wl = tid / io.E, j = tid - wl * io.E;
+        sS[wl * kMaxE + j] = temb / (1.0f + expf(-temb));  // SiLU
+      }
 
       // the tensor pipe may still be reading Y2 / Y2lo / Xlo / X[other] / W[other] of the previous pair
-      while (waited < it) { mbar_wait(bar, uint32_t(waited & 1)); ++waited; }
-      if (it + 1 < npairs) {
-        const int64_t ntile = blockIdx.x + ((it + 1) / NCHUNK) * gridDim.x;
-        tc_prefetch<Cfg>(wt, io, sX + ((it + 1) & 1) * ARR, sWc + ((it + 1) & 1) * WCH, ntile, int((it + 1) % NCHUNK), tid);
-        cp_async_commit();
+      while (waited < it) { mbar_wait(bar_mma, uint32_t(waited & 1)); ++waited; }
+      if (more) {
+        if constexpr (RESCONV) tc_prefetch_x<Cfg>(io, sX + ((it + 1) & 1) * ARR, ntile, nchunk, tid);
+        tc_prefetch_w<Cfg>(wt, sWc + ((it + 1) & 1) * WCH, nchunk, tid);
       }
+      cp_async_commit();
       named_bar_sync(2, kTcCompute);  // Y1 and sS complete
 
       // ---- A-mix   Y2[n,(t,w),c] = sum_v Y1[n,(t,v),c] * A[t][v][w]      stsgcn.py:155   (+ tf32 lo part)
@@ -358,66 +453,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
         for (int idx = tid; idx < ROWS * C4; idx += kTcCompute)
           *reinterpret_cast<float4*>(sXlo + idx * 4) = tf32_lo4(*reinterpret_cast<const float4*>(sXc + idx * 4));
       }
-      if (chunk == 0) {  // emb = Linear(SiLU(pos + cond)) for the windows of this tile
+      if (chunk == 0) {  // emb = Linear(SiLU(pos + cond)) for the windows of this tile -> sEmb[set], read by the epilogue warps
+        if (ti >= 2) mbar_wait(smem_u32(&bars[3 + set]), uint32_t((ti / 2 - 1) & 1));  // epilogue of tile ti-2 is done with it
         const int E = io.E;
         for (int i = tid; i < NW * COUT; i += kTcCompute) {
           const int wl = i / COUT, co = i - wl * COUT;
-          float e = wt.bE[co];
-          for (int j = 0; j < E; ++j) e = fmaf(wt.WEt[j * COUT + co], sS[wl * kMaxE + j], e);
-          sEmb[i] = e;
+          float e = __ldg(wt.bE + co);
+          for (int j = 0; j < E; ++j) e = fmaf(__ldg(wt.WEt + j * COUT + co), sS[wl * kMaxE + j], e);
+          sEmb[set * NW * COUT + i] = e;
         }
+        named_bar_arrive(3 + set, kTcCompute + kTcEpilogue);  // (one barrier per set: its next use is two tiles later)
       }
-      fence_proxy_async();               // generic-proxy writes (st.shared, cp.async) -> visible to the tensor pipe
-      named_bar_arrive(1, kTcThreads);   // hand the operands to the MMA warp
-
-      // ---- epilogue after the last chunk: TMEM -> bias, residual, PReLU, +emb -> channel-last store
-      if (chunk == NCHUNK - 1) {
-        named_bar_sync(2, kTcCompute);   // sEmb complete
-        while (waited < it + 1) { mbar_wait(bar, uint32_t(waited & 1)); ++waited; }
-        tc_fence_after();
-        const float slope = wt.prelu;
-        const int q = warp & 3;
-#pragma unroll 1
-        for (int m = warp >> 2; m < MT; m += 2) {
-          const int r = m * 128 + q * 32 + lane;
-          const int wl = r / P;
-          const int64_t w = tile * NW + wl;
-          const bool ok = (r < ROWS) && (w < io.n);
-          const float* embp = sEmb + (ok ? wl : 0) * COUT;
-          const int64_t grow = tile * ROWS + r;
-#pragma unroll 1
-          for (int c0 = 0; c0 < COUT; c0 += 32) {
-            uint32_t acc[32];
-            tmem_ld32(tmem + (uint32_t(q * 32) << 16) + uint32_t(m * COUT + c0), acc);
-            if (ok) {
-              float* dst = io.out + grow * COUT + c0;
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                float o[4];
-                float4 xr = make_float4(0.f, 0.f, 0.f, 0.f);
-                if constexpr (!RESCONV) xr = *reinterpret_cast<const float4*>(io.in + grow * CIN + c0 + j4 * 4);
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                  const int co = c0 + j4 * 4 + jj;
-                  float v = __uint_as_float(acc[j4 * 4 + jj]) + sBias[co];
-                  if constexpr (!RESCONV) v += f4get(xr, jj);
-                  v = v > 0.f ? v : slope * v;
-                  o[jj] = v + embp[co];
-                }
-                *reinterpret_cast<float4*>(dst + j4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
-              }
-            }
-          }
-        }
-        tc_fence_before();  // accumulator reads are ordered before the barrier that releases the next tile's MMAs
-      }
+      fence_proxy_async();                      // generic-proxy writes (st.shared, cp.async) -> visible to the tensor pipe
+      named_bar_arrive(1, kTcCompute + 32);     // hand the operands to the MMA warp
     }
   }
 
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kTcMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(uint32_t(Cfg::TMEM_COLS)) : "memory");
   }
 }
