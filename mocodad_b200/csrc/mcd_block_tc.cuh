@@ -13,27 +13,33 @@
 // accumulator (3xTF32).  tools/tc_probe.cu measures max |error| 3.3e-6 on |values| up to 12.7 at
 // K=64 against fp64 -- the class of an fp32 FMA chain (profiles/r01_tc_probe.log).
 //
-// Structure of one CTA (persistent, one per SM): 8 compute warps + 1 MMA-issuing warp + 4 epilogue warps.
-//   compute warps, per 16-channel chunk of the input:
-//     T-mix  X -> Y1, A-mix Y1 -> Y2 (fp32 FMA pipe, packed FFMA2), writing Y2 and its lo part (and the
-//     lo part of X when the block has a residual convolution) straight into the UMMA K-major
-//     SWIZZLE_64B operand layout; then fence.proxy.async + named-barrier arrive;
-//   MMA warp: waits on the named barrier, issues the chunk's tcgen05.mma's (A = activations rows x 16,
-//     B = BN-folded weights Cout x 16, D = TMEM [128 lanes x Cout] per 128-row tile), commits to an
-//     mbarrier; the tensor pipe runs while the compute warps do the T-mix of the next chunk;
-//   epilogue warps (one per TMEM lane quarter): when a tile's last commit lands they read the accumulators
-//     (tcgen05.ld 32x32b), apply bias, identity residual, PReLU and the time/condition embedding and store
-//     channel-last, while the compute warps already mix the next tile; TMEM holds two accumulator sets.
+// Structure of one CTA (persistent, one per SM), 14 warps, every hand-off through shared-memory mbarriers:
+//   warp 13     loader: cp.async of the next 16-channel activation chunk X (ring of 2-3 buffers) and one
+//               cp.async.bulk of the chunk's pre-swizzled weight operands;
+//   warps 0-3   T-mix  Y1[q,v,c] = sum_t X[t,v,c] T[v,t,q]: a thread owns (joint v, a group of output frames) and
+//               keeps its slice of the learned T matrix in REGISTERS for the whole launch, so the only shared
+//               traffic is one 16-byte activation read per 8 packed FMAs (the v2 kernel was shared-memory bound);
+//   warps 4-7   A-mix  Y2[t,w,c] = sum_v Y1[t,v,c] A[t,v,w]: a thread owns (frame t, a group of output joints) with
+//               its slice of A in registers; writes Y2 and its tf32 "lo" part (and the lo part of X for blocks
+//               with a residual convolution) straight into the UMMA K-major SWIZZLE_64B operand layout;
+//   warp 8      MMA issue: tcgen05.mma kind::tf32, A = activations [128 rows x 8], B = BN-folded weights [Cout x 8],
+//               D = TMEM [128 lanes x Cout] per 128-row tile; tcgen05.commit releases operand buffers and
+//               publishes finished accumulators;
+//   warps 9-12  epilogue (one per TMEM lane quarter): tcgen05.ld, bias, identity residual, PReLU, time/condition
+//               embedding, channel-last store -- while the other warps already work on the next tile (TMEM holds
+//               two accumulator sets).
+// T-mix of chunk c+1, A-mix of chunk c, the MMAs of chunk c-1 and the epilogue of the previous tile overlap.
 #pragma once
 #include "mcd_kernels.cuh"
 
 namespace mcd {
 
-constexpr int kTcCompute = 256;                     // compute threads (warps 0-7)
-constexpr int kTcMmaWarp = 8;                       // the MMA-issuing warp
-constexpr int kTcEpilogue = 128;                    // epilogue threads (warps 9-12: TMEM lane quarters 1,2,3,0)
-constexpr int kTcThreads = kTcCompute + 32 + kTcEpilogue;
-// named barriers: 1 = operands ready (compute -> MMA warp), 2 = compute-only sync, 3/4 = embedding of an even/odd tile ready (compute -> epilogue)
+constexpr int kTcMix = 128;        // threads per mix group (T-warps 0-3, A-warps 4-7)
+constexpr int kTcMmaWarp = 8;      // the MMA-issuing warp
+constexpr int kTcEpiWarp0 = 9;     // epilogue warps 9-12 (TMEM lane quarters 1,2,3,0)
+constexpr int kTcEpilogue = 128;
+constexpr int kTcLoadWarp = 13;    // the loader warp
+constexpr int kTcThreads = 14 * 32;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -80,6 +86,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+// cp.async completion of the executing thread counts as one (pre-counted) arrival
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
 }
@@ -119,6 +137,25 @@ __device__ __forceinline__ float4 tf32_lo4(const float4 v) {  // v - tf32_trunca
   return o;
 }
 
+// group-size chooser for the register-resident mixes: `per_window` tasks exist per window for group size g;
+// efficiency of 128 threads over NW windows
+constexpr int tc_ceil(int a, int b) { return (a + b - 1) / b; }
+constexpr int tc_eff1000(int per_window, int nw) {
+  if (per_window > kTcMix) return 0;
+  const int ws = kTcMix / per_window;           // window slots
+  const int used = ws < nw ? ws : nw;
+  const int rounds = tc_ceil(nw, used);
+  return 1000 * per_window * nw / (rounds * kTcMix);
+}
+constexpr int tc_pick_group(int outer, int inner, int nw) {  // tasks per window = outer * ceil(inner / g), g in {4,3,2}
+  int best = 4, best_eff = -1;
+  for (int g = 4; g >= 2; --g) {
+    const int e = tc_eff1000(outer * tc_ceil(inner, g), nw);
+    if (e > best_eff) { best_eff = e; best = g; }
+  }
+  return best;
+}
+
 template <int T_, int V_, int CIN_, int COUT_, int NW_>
 struct TcCfg {
   static constexpr int T = T_, V = V_, CIN = CIN_, COUT = COUT_, NW = NW_;
@@ -130,61 +167,62 @@ struct TcCfg {
   static constexpr int C4 = KC / 4;
   static constexpr bool RESCONV = CIN != COUT;
   static constexpr int NPART = RESCONV ? 4 : 2;  // weight operand parts per chunk: W hi, W lo [, Wr hi, Wr lo]
+  static constexpr int NXB = RESCONV ? 3 : 2;    // X ring depth (X is an MMA operand only with a residual convolution)
   static constexpr int VP = (V + 3) / 4 * 4;
   static constexpr int TP4 = (T + 3) / 4 * 4;
   static constexpr int TMS = T * TP4 + 4;
-  static constexpr int TQ = TP4 <= 8 ? TP4 : 8;
-  static constexpr int NQT = TP4 / TQ;
-  static constexpr int NWT = 2;
-  static constexpr int TW = VP / NWT;
+  // T-mix: thread = (window slot, joint v, group of QG output frames);  A-mix: thread = (window slot, frame t, WGS joints)
+  static constexpr int QG = T <= 4 ? T : tc_pick_group(V, T, NW);
+  static constexpr int NQG = tc_ceil(T, QG);
+  static constexpr int TT = V * NQG;                                   // T-mix tasks per window
+  static constexpr int WS_T = (kTcMix / TT) < NW ? (kTcMix / TT) : NW; // window slots
+  static constexpr int WGS = tc_pick_group(T, V, NW);
+  static constexpr int NWG = tc_ceil(V, WGS);
+  static constexpr int TA = T * NWG;
+  static constexpr int WS_A = (kTcMix / TA) < NW ? (kTcMix / TA) : NW;
+  static_assert(TT <= kTcMix && TA <= kTcMix && WS_T >= 1 && WS_A >= 1, "mix task mapping");
   static constexpr int ACC_COLS = MT * COUT;  // one accumulator set; TMEM holds two (tile parity)
   static constexpr int TMEM_COLS = 2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512);
   static_assert(CIN % KC == 0 && COUT % 32 == 0 && COUT <= 256, "tensor-core block: Cin multiple of 16, Cout multiple of 32");
   static_assert(2 * MT * COUT <= 512, "two accumulator sets exceed TMEM");
-  static_assert(TP4 % TQ == 0 && VP % (2 * NWT) == 0, "tile shapes");
+  static_assert(ROWS % 8 == 0, "operand arrays must be whole swizzle atoms");
   // shared memory carve-up, in floats from a 1024-byte aligned base
-  static constexpr int ARR = (ROWS * 16 + 127) / 128 * 128;  // operand array stride: multiple of 512 bytes
-  static constexpr int WCH = NPART * COUT * 16;              // one chunk of weight operands
-  static constexpr int SM_X = 0;                             // 2 buffers
-  static constexpr int SM_Y1 = SM_X + 2 * ARR;
-  static constexpr int SM_XLO = SM_Y1 + ARR;
-  static constexpr int SM_Y2 = SM_XLO + (RESCONV ? ARR : 0);
-  static constexpr int SM_Y2LO = SM_Y2 + ARR;
-  static constexpr int SM_WC = SM_Y2LO + ARR;                // 2 buffers; also absorbs the last tile's over-read
-  static constexpr int SM_A = SM_WC + 2 * WCH;
-  static constexpr int SM_TM = SM_A + T * V * VP;
-  static constexpr int SM_BIAS = SM_TM + V * TMS;
+  static constexpr int ARR = ROWS * 16;          // one operand array [ROWS][16] (a multiple of 512 bytes)
+  static constexpr int WCH = NPART * COUT * 16;  // one chunk of weight operands
+  static constexpr int SM_X = 0;                 // NXB buffers
+  static constexpr int SM_Y1 = SM_X + NXB * ARR;  // 2
+  static constexpr int SM_XLO = SM_Y1 + 2 * ARR;  // 1 (residual convolution only)
+  static constexpr int SM_Y2 = SM_XLO + (RESCONV ? ARR : 0);  // 2
+  static constexpr int SM_Y2LO = SM_Y2 + 2 * ARR;             // 2
+  static constexpr int SM_WC = SM_Y2LO + 2 * ARR;             // 2; also absorbs the last tile's over-read
+  static constexpr int SM_BIAS = SM_WC + 2 * WCH;
   static constexpr int SM_EMB = SM_BIAS + COUT;
-  static constexpr int SM_S = SM_EMB + 2 * NW * COUT;  // sEmb is double-buffered like the accumulators
+  static constexpr int SM_S = SM_EMB + NW * COUT;
   static constexpr int SM_TOTAL = SM_S + NW * kMaxE;
-  static_assert((MT * 128 - ROWS) * 16 <= 2 * WCH + T * V * VP, "over-read of the last MMA tile must stay inside the allocation");
+  static_assert((MT * 128 - ROWS) * 16 <= 2 * WCH, "over-read of the last MMA tile must stay inside the allocation");
   static constexpr size_t SMEM_BYTES = size_t(SM_TOTAL) * sizeof(float) + 1024;  // + alignment slack
 };
 
-template <class Cfg>
-__device__ __forceinline__ void tc_prefetch_x(const BlockIO& io, float* sXbuf, int64_t tile, int chunk, int tid) {
-  const int64_t row0 = tile * Cfg::ROWS;
-  const int64_t nrows = io.n * Cfg::P;
-  const float* base = io.in + chunk * Cfg::KC;
-  for (int idx = tid; idx < Cfg::ROWS * Cfg::C4; idx += kTcCompute) {
-    const int r = idx >> 2, j = idx & 3;
-    const bool ok = (row0 + r) < nrows;
-    const float* src = ok ? base + (row0 + r) * Cfg::CIN + j * 4 : io.in;
-    cp_async16(sXbuf + sw_off(r, j), src, ok);
-  }
-}
-template <class Cfg>
-__device__ __forceinline__ void tc_prefetch_w(const BlockWeights& wt, float* sWbuf, int chunk, int tid) {
-  const float* wsrc = wt.Bop + size_t(chunk) * Cfg::WCH;
-  for (int idx = tid; idx < Cfg::WCH / 4; idx += kTcCompute) cp_async16(sWbuf + idx * 4, wsrc + idx * 4, true);
-}
+// barrier slots in shared memory
+enum TcBar {
+  BAR_X_FULL = 0,                 // [3] loader -> T-warps (and A-warps / MMA with a residual convolution)
+  BAR_X_EMPTY = 3,                // [3] consumers -> loader
+  BAR_W_FULL = 6,                 // [2] loader (bulk copy) -> MMA warp
+  BAR_Y1_FULL = 8,                // [2] T-warps -> A-warps
+  BAR_Y1_EMPTY = 10,              // [2] A-warps -> T-warps
+  BAR_OPS_FULL = 12,              // [2] A-warps -> MMA warp
+  BAR_MMA_DONE = 14,              // [2] tcgen05.commit -> A-warps, loader (operand buffers free)
+  BAR_ACC_FULL = 16,              // [2] tcgen05.commit -> epilogue
+  BAR_ACC_EMPTY = 18,             // [2] epilogue -> MMA warp
+  BAR_COUNT = 20
+};
 
 template <class Cfg>
 __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const BlockWeights wt, const BlockIO io) {
   constexpr int T = Cfg::T, V = Cfg::V, P = Cfg::P, ROWS = Cfg::ROWS, C4 = Cfg::C4, MT = Cfg::MT;
-  constexpr int CIN = Cfg::CIN, COUT = Cfg::COUT, NCHUNK = Cfg::NCHUNK, NW = Cfg::NW;
+  constexpr int CIN = Cfg::CIN, COUT = Cfg::COUT, NCHUNK = Cfg::NCHUNK, NW = Cfg::NW, NXB = Cfg::NXB;
   constexpr int VP = Cfg::VP, TP4 = Cfg::TP4, TMS = Cfg::TMS, ARR = Cfg::ARR, WCH = Cfg::WCH;
-  constexpr int TQ = Cfg::TQ, NQT = Cfg::NQT, TW = Cfg::TW, NWT = Cfg::NWT;
+  constexpr int QG = Cfg::QG, NQG = Cfg::NQG, WGS = Cfg::WGS, NWG = Cfg::NWG;
   constexpr bool RESCONV = Cfg::RESCONV;
 
   extern __shared__ uint8_t smem_raw[];
@@ -196,13 +234,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
   float* sY2 = smem + Cfg::SM_Y2;
   float* sY2lo = smem + Cfg::SM_Y2LO;
   float* sWc = smem + Cfg::SM_WC;
-  float* sA = smem + Cfg::SM_A;
-  float* sTm = smem + Cfg::SM_TM;
   float* sBias = smem + Cfg::SM_BIAS;
   float* sEmb = smem + Cfg::SM_EMB;
   float* sS = smem + Cfg::SM_S;
-  // mbarriers: [0] per-pair MMA commit (operand buffers free), [1],[2] accumulator set full, [3],[4] set drained
-  __shared__ __align__(8) uint64_t bars[5];
+  __shared__ __align__(8) uint64_t bars[BAR_COUNT];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -210,6 +245,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
   if (int64_t(blockIdx.x) >= ntiles) return;  // uniform over the CTA
   const int my_tiles = int((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
   const int npairs = my_tiles * NCHUNK;
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  auto BAR = [&](int slot) { return bar0 + uint32_t(slot) * 8u; };
 
   // ---- once per CTA ----
   if (warp == kTcMmaWarp) {
@@ -217,42 +254,158 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
                  "r"(uint32_t(Cfg::TMEM_COLS))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  } else if (warp < kTcMmaWarp) {
-    if (tid == 0) {
-      mbar_init(smem_u32(&bars[0]), 1);
-      mbar_init(smem_u32(&bars[1]), 1);
-      mbar_init(smem_u32(&bars[2]), 1);
-      mbar_init(smem_u32(&bars[3]), kTcEpilogue);
-      mbar_init(smem_u32(&bars[4]), kTcEpilogue);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (tid == 0) {
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(BAR(BAR_X_FULL + i), 32);
+      mbar_init(BAR(BAR_X_EMPTY + i), RESCONV ? 2 * kTcMix + 1 : kTcMix);
     }
-    static_assert((T * V * VP) % 4 == 0 && (V * TMS) % 4 == 0 && COUT % 4 == 0, "16-byte weight copies");
-    for (int i = tid; i < T * V * VP / 4; i += kTcCompute) cp_async16(sA + i * 4, wt.A + i * 4, true);
-    for (int i = tid; i < V * TMS / 4; i += kTcCompute) cp_async16(sTm + i * 4, wt.Tm + i * 4, true);
-    cp_async_commit();  // waited for together with the first activation chunk
-  } else {
-    for (int i = tid - (kTcCompute + 32); i < COUT; i += kTcEpilogue) sBias[i] = wt.bias[i];
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(BAR(BAR_W_FULL + i), 1);
+      mbar_init(BAR(BAR_Y1_FULL + i), kTcMix);
+      mbar_init(BAR(BAR_Y1_EMPTY + i), kTcMix);
+      mbar_init(BAR(BAR_OPS_FULL + i), kTcMix);
+      mbar_init(BAR(BAR_MMA_DONE + i), 1);
+      mbar_init(BAR(BAR_ACC_FULL + i), 1);
+      mbar_init(BAR(BAR_ACC_EMPTY + i), kTcEpilogue);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (warp >= kTcEpiWarp0 && warp < kTcLoadWarp)
+    for (int i = tid - kTcEpiWarp0 * 32; i < COUT; i += kTcEpilogue) sBias[i] = wt.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t bar_mma = smem_u32(&bars[0]);
 
-  if (warp == kTcMmaWarp) {
+  if (warp < 4) {
+    // =============================== T-mix warps ===============================
+    // Y1[n,(q,v),c] = sum_t X[n,(t,v),c] * Tm[v][t][q]        stsgcn.py:154
+    const int ws = tid / Cfg::TT, rem = tid - ws * Cfg::TT;
+    const int v = rem / NQG, qg = rem - v * NQG;
+    const bool active = ws < Cfg::WS_T;
+    float wT[T][QG];  // this thread's slice of the learned time-mix matrix, resident for the whole launch
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+      for (int q = 0; q < QG; ++q)
+        wT[t][q] = (active && qg * QG + q < T) ? __ldg(wt.Tm + v * TMS + t * TP4 + qg * QG + q) : 0.f;
+
+    for (int it = 0; it < npairs; ++it) {
+      const int b = it % NXB, s = it & 1;
+      mbar_wait(BAR(BAR_X_FULL + b), uint32_t((it / NXB) & 1));
+      if (it >= 2) mbar_wait(BAR(BAR_Y1_EMPTY + s), uint32_t((it / 2 - 1) & 1));
+      if (active) {
+        const float* sXc = sX + b * ARR;
+        float* sY = sY1 + s * ARR;
+        for (int wl = ws; wl < NW; wl += Cfg::WS_T) {
+          const int r0 = wl * P + v;
+#pragma unroll 1
+          for (int c4 = 0; c4 < C4; ++c4) {
+            float2 a[2][QG];
+#pragma unroll
+            for (int q = 0; q < QG; ++q) a[0][q] = a[1][q] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              const float4 x = *reinterpret_cast<const float4*>(sXc + sw_off(r0 + t * V, c4));
+              const float2 xlo = make_float2(x.x, x.y), xhi = make_float2(x.z, x.w);
+#pragma unroll
+              for (int q = 0; q < QG; ++q) {
+                const float2 ww = make_float2(wT[t][q], wT[t][q]);
+                a[0][q] = ffma2(xlo, ww, a[0][q]);
+                a[1][q] = ffma2(xhi, ww, a[1][q]);
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < QG; ++q) {
+              const int qq = qg * QG + q;
+              if (qq < T)
+                *reinterpret_cast<float4*>(sY + sw_off(r0 + qq * V, c4)) = make_float4(a[0][q].x, a[0][q].y, a[1][q].x, a[1][q].y);
+            }
+          }
+        }
+      }
+      mbar_arrive(BAR(BAR_Y1_FULL + s));
+      mbar_arrive(BAR(BAR_X_EMPTY + b));
+    }
+  } else if (warp < 8) {
+    // =============================== A-mix warps ===============================
+    // Y2[n,(t,w),c] = sum_v Y1[n,(t,v),c] * A[t][v][w]       stsgcn.py:155   (+ tf32 lo parts for the tensor pipe)
+    const int atid = tid - kTcMix;
+    const int ws = atid / Cfg::TA, rem = atid - ws * Cfg::TA;
+    const int t = rem / NWG, wg = rem - t * NWG;
+    const bool active = ws < Cfg::WS_A;
+    float wA[V][WGS];  // this thread's slice of the learned joint-mix matrix
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+      for (int j = 0; j < WGS; ++j)
+        wA[v][j] = (active && wg * WGS + j < V) ? __ldg(wt.A + (t * V + v) * VP + wg * WGS + j) : 0.f;
+
+    for (int it = 0; it < npairs; ++it) {
+      const int b = it % NXB, s = it & 1;
+      mbar_wait(BAR(BAR_Y1_FULL + s), uint32_t((it / 2) & 1));
+      if (it >= 2) mbar_wait(BAR(BAR_MMA_DONE + s), uint32_t((it / 2 - 1) & 1));  // Y2[s], Y2lo[s] free again
+      if (active) {
+        const float* sY = sY1 + s * ARR;
+        float* sZ = sY2 + s * ARR;
+        float* sZlo = sY2lo + s * ARR;
+        for (int wl = ws; wl < NW; wl += Cfg::WS_A) {
+          const int r0 = wl * P + t * V;
+#pragma unroll 1
+          for (int c4 = 0; c4 < C4; ++c4) {
+            float2 a[2][WGS];
+#pragma unroll
+            for (int j = 0; j < WGS; ++j) a[0][j] = a[1][j] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              const float4 y = *reinterpret_cast<const float4*>(sY + sw_off(r0 + v, c4));
+              const float2 ylo = make_float2(y.x, y.y), yhi = make_float2(y.z, y.w);
+#pragma unroll
+              for (int j = 0; j < WGS; ++j) {
+                const float2 ww = make_float2(wA[v][j], wA[v][j]);
+                a[0][j] = ffma2(ylo, ww, a[0][j]);
+                a[1][j] = ffma2(yhi, ww, a[1][j]);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < WGS; ++j) {
+              const int w = wg * WGS + j;
+              if (w < V) {
+                const float4 o = make_float4(a[0][j].x, a[0][j].y, a[1][j].x, a[1][j].y);
+                const int off = sw_off(r0 + w, c4);
+                *reinterpret_cast<float4*>(sZ + off) = o;
+                *reinterpret_cast<float4*>(sZlo + off) = tf32_lo4(o);
+              }
+            }
+          }
+        }
+      }
+      mbar_arrive(BAR(BAR_Y1_EMPTY + s));
+      if constexpr (RESCONV) {  // lo part of X for the residual convolution (elementwise: the layouts coincide)
+        mbar_wait(BAR(BAR_X_FULL + b), uint32_t((it / NXB) & 1));
+        if (it >= 1) mbar_wait(BAR(BAR_MMA_DONE + ((it - 1) & 1)), uint32_t(((it - 1) / 2) & 1));  // single Xlo buffer
+        const float* sXc = sX + b * ARR;
+        for (int idx = atid; idx < ROWS * C4; idx += kTcMix)
+          *reinterpret_cast<float4*>(sXlo + idx * 4) = tf32_lo4(*reinterpret_cast<const float4*>(sXc + idx * 4));
+        mbar_arrive(BAR(BAR_X_EMPTY + b));
+      }
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor pipe
+      mbar_arrive(BAR(BAR_OPS_FULL + s));
+    }
+  } else if (warp == kTcMmaWarp) {
     // =============================== MMA-issuing warp ===============================
     const uint32_t idesc = umma_idesc_tf32(COUT);
     for (int it = 0; it < npairs; ++it) {
       const int ti = it / NCHUNK, chunk = it - ti * NCHUNK;
-      const int set = ti & 1;
-      named_bar_sync(1, kTcCompute + 32);  // operands of pair `it` are in shared memory (compute warps fenced + arrived)
-      if (chunk == 0 && ti >= 2) mbar_wait(smem_u32(&bars[3 + set]), uint32_t((ti / 2 - 1) & 1));  // set drained by the epilogue
+      const int set = ti & 1, s = it & 1, b = it % NXB;
+      mbar_wait(BAR(BAR_OPS_FULL + s), uint32_t((it / 2) & 1));
+      mbar_wait(BAR(BAR_W_FULL + s), uint32_t((it / 2) & 1));
+      if (chunk == 0 && ti >= 2) mbar_wait(BAR(BAR_ACC_EMPTY + set), uint32_t((ti / 2 - 1) & 1));  // set drained by the epilogue
       tc_fence_after();
       if (lane == 0) {
-        const int buf = it & 1;
-        const uint32_t aY2 = smem_u32(sY2), aY2lo = smem_u32(sY2lo);
-        const uint32_t aX = smem_u32(sX + buf * ARR), aXlo = smem_u32(sXlo);
-        const uint32_t bW = smem_u32(sWc + buf * WCH);
+        const uint32_t aY2 = smem_u32(sY2 + s * ARR), aY2lo = smem_u32(sY2lo + s * ARR);
+        const uint32_t aX = smem_u32(sX + b * ARR), aXlo = smem_u32(sXlo);
+        const uint32_t bW = smem_u32(sWc + s * WCH);
         constexpr uint32_t PART = COUT * 64;  // bytes per weight part
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
@@ -273,21 +426,67 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
             }
           }
         }
-        umma_commit(bar_mma);
-        if (chunk == NCHUNK - 1) umma_commit(smem_u32(&bars[1 + set]));  // the tile's accumulators are complete
+        umma_commit(BAR(BAR_MMA_DONE + s));
+        if constexpr (RESCONV) umma_commit(BAR(BAR_X_EMPTY + b));
+        if (chunk == NCHUNK - 1) umma_commit(BAR(BAR_ACC_FULL + set));  // the tile's accumulators are complete
       }
       __syncwarp();
     }
-  } else if (warp > kTcMmaWarp) {
+  } else if (warp == kTcLoadWarp) {
+    // =============================== loader warp ===============================
+    const int64_t nrows = io.n * P;
+    for (int it = 0; it < npairs; ++it) {
+      const int ti = it / NCHUNK, chunk = it - ti * NCHUNK;
+      const int64_t tile = blockIdx.x + int64_t(ti) * gridDim.x;
+      const int b = it % NXB, s = it & 1;
+      if (it >= NXB) mbar_wait(BAR(BAR_X_EMPTY + b), uint32_t((it / NXB - 1) & 1));
+      {
+        float* dstb = sX + b * ARR;
+        const int64_t row0 = tile * ROWS;
+        const float* base = io.in + chunk * Cfg::KC;
+        for (int idx = lane; idx < ROWS * C4; idx += 32) {
+          const int r = idx >> 2, j = idx & 3;
+          const bool ok = (row0 + r) < nrows;
+          const float* src = ok ? base + (row0 + r) * CIN + j * 4 : io.in;
+          cp_async16(dstb + sw_off(r, j), src, ok);
+        }
+        cp_async_mbar_arrive_noinc(BAR(BAR_X_FULL + b));
+      }
+      if (it >= 2) mbar_wait(BAR(BAR_MMA_DONE + s), uint32_t((it / 2 - 1) & 1));  // W[s] free again
+      if (lane == 0) {
+        mbar_expect_tx(BAR(BAR_W_FULL + s), uint32_t(WCH * 4));
+        bulk_g2s(smem_u32(sWc + s * WCH), wt.Bop + size_t(chunk) * WCH, uint32_t(WCH * 4), BAR(BAR_W_FULL + s));
+      }
+      __syncwarp();
+    }
+    cp_async_wait_all();
+  } else {
     // =============================== epilogue warps ===============================
-    // TMEM -> bias, identity residual, PReLU, + emb -> channel-last store            stsgcn.py:109-114
+    // TMEM -> bias, identity residual, PReLU, + Linear(SiLU(pos + cond)) -> channel-last store      stsgcn.py:109-114
     const float slope = wt.prelu;
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int etid = tid - kTcEpiWarp0 * 32;
+    const int E = io.E;
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int64_t tile = blockIdx.x + int64_t(ti) * gridDim.x;
       const int set = ti & 1;
-      named_bar_sync(3 + set, kTcCompute + kTcEpilogue);  // sEmb[set] of this tile is written
-      mbar_wait(smem_u32(&bars[1 + set]), uint32_t((ti / 2) & 1));
+      named_bar_sync(2, kTcEpilogue);  // everyone is done with the previous tile's sEmb
+      for (int i = etid; i < NW * E; i += kTcEpilogue) {
+        const int wl = i / E, j = i - wl * E;
+        const int64_t w = tile * NW + wl;
+        float v = __ldg(io.pos + j);
+        if (io.cond != nullptr && w < io.n) v += __ldg(io.cond + ((io.w0 + w) % io.condB) * E + j);
+        sS[wl * kMaxE + j] = v / (1.0f + expf(-v));  // SiLU
+      }
+      named_bar_sync(2, kTcEpilogue);
+      for (int i = etid; i < NW * COUT; i += kTcEpilogue) {
+        const int wl = i / COUT, co = i - wl * COUT;
+        float e = __ldg(wt.bE + co);
+        for (int j = 0; j < E; ++j) e = fmaf(__ldg(wt.WEt + j * COUT + co), sS[wl * kMaxE + j], e);
+        sEmb[i] = e;
+      }
+      named_bar_sync(2, kTcEpilogue);
+      mbar_wait(BAR(BAR_ACC_FULL + set), uint32_t((ti / 2) & 1));
       tc_fence_after();
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
@@ -295,7 +494,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
         const int wl = r / P;
         const int64_t w = tile * NW + wl;
         const bool ok = (r < ROWS) && (w < io.n);
-        const float* embp = sEmb + (set * NW + (ok ? wl : 0)) * COUT;
+        const float* embp = sEmb + (ok ? wl : 0) * COUT;
         const int64_t grow = tile * ROWS + r;
 #pragma unroll 1
         for (int c0 = 0; c0 < COUT; c0 += 32) {
@@ -324,148 +523,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
           }
         }
       }
-      tc_fence_before();                   // accumulator reads ordered before the release of the set
-      mbar_arrive(smem_u32(&bars[3 + set]));
-    }
-  } else {
-    // =============================== compute warps ===============================
-    tc_prefetch_x<Cfg>(io, sX, blockIdx.x, 0, tid);
-    tc_prefetch_w<Cfg>(wt, sWc, 0, tid);
-    cp_async_commit();
-    int waited = 0;  // per-pair MMA commits observed so far
-
-    for (int it = 0; it < npairs; ++it) {
-      const int ti = it / NCHUNK, chunk = it - ti * NCHUNK;
-      const int64_t tile = blockIdx.x + int64_t(ti) * gridDim.x;
-      const int set = ti & 1;
-      float* sXc = sX + (it & 1) * ARR;
-      const bool more = it + 1 < npairs;
-      const int nti = (it + 1) / NCHUNK, nchunk = (it + 1) - nti * NCHUNK;
-      const int64_t ntile = blockIdx.x + int64_t(nti) * gridDim.x;
-
-      cp_async_wait_all();
-      named_bar_sync(2, kTcCompute);  // X / W chunk visible; the previous pair's mix finished everywhere
-
-      // identity blocks: X is not an MMA operand, so its other buffer is free now -- prefetch a whole pair ahead
-      if constexpr (!RESCONV) {
-        if (more) tc_prefetch_x<Cfg>(io, sX + ((it + 1) & 1) * ARR, ntile, nchunk, tid);
-      }
-
-      // time/condition embedding input  pos + cond (stsgcn.py:112-114), once per tile: the global loads are
-      // issued here and consumed after the T-mix, which hides their latency
-      float temb = 0.f;
-      if (chunk == 0 && tid < NW * io.E) {
-        const int wl = tid / io.E, j = tid - wl * io.E;
-        const int64_t w = tile * NW + wl;
-        temb = __ldg(io.pos + j);
-        if (io.cond != nullptr && w < io.n) temb += __ldg(io.cond + ((io.w0 + w) % io.condB) * io.E + j);
-      }
-
-      // ---- T-mix   Y1[n,(q,v),c] = sum_t X[n,(t,v),c] * Tm[v][t][q]     stsgcn.py:154
-      for (int task = tid; task < NQT * NW * V * C4; task += kTcCompute) {
-        const int c4 = task % C4;
-        const int col = (task / C4) % (NW * V);
-        const int qt = task / (C4 * NW * V);
-        const int wl = col / V, v = col - wl * V;
-        float2 a[2][TQ];
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int q = 0; q < TQ; ++q) a[c][q] = make_float2(0.f, 0.f);
-        const float* tp = sTm + v * TMS + qt * TQ;
-        const int r0 = wl * P + v;
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-          const float4 x = *reinterpret_cast<const float4*>(sXc + sw_off(r0 + t * V, c4));
-          const float2 xlo = make_float2(x.x, x.y), xhi = make_float2(x.z, x.w);
-#pragma unroll
-          for (int q4 = 0; q4 < TQ / 4; ++q4) {
-            const float4 w = *reinterpret_cast<const float4*>(tp + t * TP4 + q4 * 4);
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-              const float wv = f4get(w, qq);
-              const float2 ww = make_float2(wv, wv);
-              a[0][q4 * 4 + qq] = ffma2(xlo, ww, a[0][q4 * 4 + qq]);
-              a[1][q4 * 4 + qq] = ffma2(xhi, ww, a[1][q4 * 4 + qq]);
-            }
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < TQ; ++q) {
-          const int qq = qt * TQ + q;
-          if (qq < T)
-            *reinterpret_cast<float4*>(sY1 + sw_off(r0 + qq * V, c4)) = make_float4(a[0][q].x, a[0][q].y, a[1][q].x, a[1][q].y);
-        }
-      }
-      if (chunk == 0 && tid < NW * io.E) {
-        const int wl = tid / io.E, j = tid - wl * io.E;
-        sS[wl * kMaxE + j] = temb / (1.0f + expf(-temb));  // SiLU
-      }
-
-      // the tensor pipe may still be reading Y2 / Y2lo / Xlo / X[other] / W[other] of the previous pair
-      while (waited < it) { mbar_wait(bar_mma, uint32_t(waited & 1)); ++waited; }
-      if (more) {
-        if constexpr (RESCONV) tc_prefetch_x<Cfg>(io, sX + ((it + 1) & 1) * ARR, ntile, nchunk, tid);
-        tc_prefetch_w<Cfg>(wt, sWc + ((it + 1) & 1) * WCH, nchunk, tid);
-      }
-      cp_async_commit();
-      named_bar_sync(2, kTcCompute);  // Y1 and sS complete
-
-      // ---- A-mix   Y2[n,(t,w),c] = sum_v Y1[n,(t,v),c] * A[t][v][w]      stsgcn.py:155   (+ tf32 lo part)
-      for (int task = tid; task < NW * T * NWT * C4; task += kTcCompute) {
-        const int c4 = task % C4;
-        const int wtile = (task / C4) % NWT;
-        const int row = task / (C4 * NWT);
-        const int wl = row / T, q = row - wl * T;
-        float2 a[2][TW];
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int j = 0; j < TW; ++j) a[c][j] = make_float2(0.f, 0.f);
-        const int r0 = wl * P + q * V;
-        const float* ap = sA + q * V * VP + wtile * TW;
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          const float4 y = *reinterpret_cast<const float4*>(sY1 + sw_off(r0 + v, c4));
-          const float2 ylo = make_float2(y.x, y.y), yhi = make_float2(y.z, y.w);
-#pragma unroll
-          for (int j2 = 0; j2 < TW / 2; ++j2) {
-            const float2 w = *reinterpret_cast<const float2*>(ap + v * VP + j2 * 2);
-            const float2 w0 = make_float2(w.x, w.x), w1 = make_float2(w.y, w.y);
-            a[0][j2 * 2] = ffma2(ylo, w0, a[0][j2 * 2]);
-            a[1][j2 * 2] = ffma2(yhi, w0, a[1][j2 * 2]);
-            a[0][j2 * 2 + 1] = ffma2(ylo, w1, a[0][j2 * 2 + 1]);
-            a[1][j2 * 2 + 1] = ffma2(yhi, w1, a[1][j2 * 2 + 1]);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < TW; ++j) {
-          const int w = wtile * TW + j;
-          if (w < V) {
-            const float4 o = make_float4(a[0][j].x, a[0][j].y, a[1][j].x, a[1][j].y);
-            const int off = sw_off(r0 + w, c4);
-            *reinterpret_cast<float4*>(sY2 + off) = o;
-            *reinterpret_cast<float4*>(sY2lo + off) = tf32_lo4(o);
-          }
-        }
-      }
-      if constexpr (RESCONV) {  // lo part of X for the residual convolution (elementwise: the layouts coincide)
-        for (int idx = tid; idx < ROWS * C4; idx += kTcCompute)
-          *reinterpret_cast<float4*>(sXlo + idx * 4) = tf32_lo4(*reinterpret_cast<const float4*>(sXc + idx * 4));
-      }
-      if (chunk == 0) {  // emb = Linear(SiLU(pos + cond)) for the windows of this tile -> sEmb[set], read by the epilogue warps
-        if (ti >= 2) mbar_wait(smem_u32(&bars[3 + set]), uint32_t((ti / 2 - 1) & 1));  // epilogue of tile ti-2 is done with it
-        const int E = io.E;
-        for (int i = tid; i < NW * COUT; i += kTcCompute) {
-          const int wl = i / COUT, co = i - wl * COUT;
-          float e = __ldg(wt.bE + co);
-          for (int j = 0; j < E; ++j) e = fmaf(__ldg(wt.WEt + j * COUT + co), sS[wl * kMaxE + j], e);
-          sEmb[set * NW * COUT + i] = e;
-        }
-        named_bar_arrive(3 + set, kTcCompute + kTcEpilogue);  // (one barrier per set: its next use is two tiles later)
-      }
-      fence_proxy_async();                      // generic-proxy writes (st.shared, cp.async) -> visible to the tensor pipe
-      named_bar_arrive(1, kTcCompute + 32);     // hand the operands to the MMA warp
+      tc_fence_before();  // accumulator reads ordered before the release of the set
+      mbar_arrive(BAR(BAR_ACC_EMPTY + set));
     }
   }
 
