@@ -13,7 +13,8 @@
 // accumulator (3xTF32).  tools/tc_probe.cu measures max |error| 3.3e-6 on |values| up to 12.7 at
 // K=64 against fp64 -- the class of an fp32 FMA chain (profiles/r01_tc_probe.log).
 //
-// Structure of one CTA (persistent, one per SM), 14 warps, every hand-off through shared-memory mbarriers:
+// Structure of one CTA (persistent, one per SM), 4 warpgroups (register budgets re-balanced with setmaxnreg),
+// every hand-off through shared-memory mbarriers:
 //   warp 13     loader: cp.async of the next 16-channel activation chunk X (ring of 2-3 buffers) and one
 //               cp.async.bulk of the chunk's pre-swizzled weight operands;
 //   warps 0-3   T-mix  Y1[q,v,c] = sum_t X[t,v,c] T[v,t,q]: a thread owns (joint v, a group of output frames) and
@@ -22,10 +23,10 @@
 //   warps 4-7   A-mix  Y2[t,w,c] = sum_v Y1[t,v,c] A[t,v,w]: a thread owns (frame t, a group of output joints) with
 //               its slice of A in registers; writes Y2 and its tf32 "lo" part (and the lo part of X for blocks
 //               with a residual convolution) straight into the UMMA K-major SWIZZLE_64B operand layout;
-//   warp 8      MMA issue: tcgen05.mma kind::tf32, A = activations [128 rows x 8], B = BN-folded weights [Cout x 8],
+//   warp 12     MMA issue: tcgen05.mma kind::tf32, A = activations [128 rows x 8], B = BN-folded weights [Cout x 8],
 //               D = TMEM [128 lanes x Cout] per 128-row tile; tcgen05.commit releases operand buffers and
 //               publishes finished accumulators;
-//   warps 9-12  epilogue (one per TMEM lane quarter): tcgen05.ld, bias, identity residual, PReLU, time/condition
+//   warps 8-11  epilogue (one per TMEM lane quarter): tcgen05.ld, bias, identity residual, PReLU, time/condition
 //               embedding, channel-last store -- while the other warps already work on the next tile (TMEM holds
 //               two accumulator sets).
 // T-mix of chunk c+1, A-mix of chunk c, the MMAs of chunk c-1 and the epilogue of the previous tile overlap.
@@ -35,11 +36,16 @@
 namespace mcd {
 
 constexpr int kTcMix = 128;        // threads per mix group (T-warps 0-3, A-warps 4-7)
-constexpr int kTcMmaWarp = 8;      // the MMA-issuing warp
-constexpr int kTcEpiWarp0 = 9;     // epilogue warps 9-12 (TMEM lane quarters 1,2,3,0)
+constexpr int kTcEpiWarp0 = 8;     // epilogue warps 8-11 (TMEM lane quarters 0,1,2,3)
+constexpr int kTcMmaWarp = 12;     // the MMA-issuing warp
 constexpr int kTcEpilogue = 128;
-constexpr int kTcLoadWarp = 13;    // the loader warp
-constexpr int kTcThreads = 14 * 32;
+constexpr int kTcLoadWarp = 13;    // the loader warp (warps 14-15 only pad the last warpgroup)
+constexpr int kTcThreads = 16 * 32;
+// Register budgets per warpgroup (setmaxnreg): the T-mix threads keep 96 weights + two accumulator sets in registers.
+constexpr int kRegsT = 184, kRegsA = 144, kRegsE = 112, kRegsS = 64;
+static_assert(kRegsT + kRegsA + kRegsE + kRegsS <= 512, "one warp of each group shares an SM sub-partition (16K registers)");
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -188,10 +194,15 @@ struct TcCfg {
   static_assert(ROWS % 8 == 0, "operand arrays must be whole swizzle atoms");
   // shared memory carve-up, in floats from a 1024-byte aligned base
   static constexpr int ARR = ROWS * 16;          // one operand array [ROWS][16] (a multiple of 512 bytes)
+  // Y1 is not an MMA operand, so its layout is chosen for the two mixes: 16-byte (4-channel) elements indexed
+  // [window][c4][q within the frame group][T-mix thread (v, qg)] with the thread pitch TTP = 2 (mod 8): the T-mix
+  // threads of a warp store consecutive elements, the A-mix threads of a warp (consecutive frames) hit distinct banks
+  static constexpr int TTP = T >= 8 ? (TT + 5) / 8 * 8 + 2 : (TT | 1);
+  static constexpr int Y1ARR = ((NW * 4 * QG * TTP * 4) + 127) / 128 * 128;
   static constexpr int WCH = NPART * COUT * 16;  // one chunk of weight operands
   static constexpr int SM_X = 0;                 // NXB buffers
   static constexpr int SM_Y1 = SM_X + NXB * ARR;  // 2
-  static constexpr int SM_XLO = SM_Y1 + 2 * ARR;  // 1 (residual convolution only)
+  static constexpr int SM_XLO = SM_Y1 + 2 * Y1ARR;  // 1 (residual convolution only)
   static constexpr int SM_Y2 = SM_XLO + (RESCONV ? ARR : 0);  // 2
   static constexpr int SM_Y2LO = SM_Y2 + 2 * ARR;             // 2
   static constexpr int SM_WC = SM_Y2LO + 2 * ARR;             // 2; also absorbs the last tile's over-read
@@ -222,7 +233,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
   constexpr int T = Cfg::T, V = Cfg::V, P = Cfg::P, ROWS = Cfg::ROWS, C4 = Cfg::C4, MT = Cfg::MT;
   constexpr int CIN = Cfg::CIN, COUT = Cfg::COUT, NCHUNK = Cfg::NCHUNK, NW = Cfg::NW, NXB = Cfg::NXB;
   constexpr int VP = Cfg::VP, TP4 = Cfg::TP4, TMS = Cfg::TMS, ARR = Cfg::ARR, WCH = Cfg::WCH;
-  constexpr int QG = Cfg::QG, NQG = Cfg::NQG, WGS = Cfg::WGS, NWG = Cfg::NWG;
+  constexpr int QG = Cfg::QG, NQG = Cfg::NQG, WGS = Cfg::WGS, NWG = Cfg::NWG, TTP = Cfg::TTP, Y1ARR = Cfg::Y1ARR;
   constexpr bool RESCONV = Cfg::RESCONV;
 
   extern __shared__ uint8_t smem_raw[];
@@ -279,6 +290,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
 
   if (warp < 4) {
     // =============================== T-mix warps ===============================
+    reg_inc<kRegsT>();
     // Y1[n,(q,v),c] = sum_t X[n,(t,v),c] * Tm[v][t][q]        stsgcn.py:154
     const int ws = tid / Cfg::TT, rem = tid - ws * Cfg::TT;
     const int v = rem / NQG, qg = rem - v * NQG;
@@ -296,30 +308,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       if (it >= 2) mbar_wait(BAR(BAR_Y1_EMPTY + s), uint32_t((it / 2 - 1) & 1));
       if (active) {
         const float* sXc = sX + b * ARR;
-        float* sY = sY1 + s * ARR;
+        float* sY = sY1 + s * Y1ARR;
         for (int wl = ws; wl < NW; wl += Cfg::WS_T) {
           const int r0 = wl * P + v;
 #pragma unroll 1
-          for (int c4 = 0; c4 < C4; ++c4) {
-            float2 a[2][QG];
+          for (int cp = 0; cp < C4; cp += 2) {  // two 4-channel groups at once: two independent load streams
+            float2 a[2][2][QG];
 #pragma unroll
-            for (int q = 0; q < QG; ++q) a[0][q] = a[1][q] = make_float2(0.f, 0.f);
+            for (int q = 0; q < QG; ++q) a[0][0][q] = a[0][1][q] = a[1][0][q] = a[1][1][q] = make_float2(0.f, 0.f);
+            float4 xn0 = *reinterpret_cast<const float4*>(sXc + sw_off(r0, cp));
+            float4 xn1 = *reinterpret_cast<const float4*>(sXc + sw_off(r0, cp + 1));
 #pragma unroll
             for (int t = 0; t < T; ++t) {
-              const float4 x = *reinterpret_cast<const float4*>(sXc + sw_off(r0 + t * V, c4));
-              const float2 xlo = make_float2(x.x, x.y), xhi = make_float2(x.z, x.w);
+              const float4 x0 = xn0, x1 = xn1;
+              if (t + 1 < T) {  // next frame in flight
+                xn0 = *reinterpret_cast<const float4*>(sXc + sw_off(r0 + (t + 1) * V, cp));
+                xn1 = *reinterpret_cast<const float4*>(sXc + sw_off(r0 + (t + 1) * V, cp + 1));
+              }
+              const float2 x0l = make_float2(x0.x, x0.y), x0h = make_float2(x0.z, x0.w);
+              const float2 x1l = make_float2(x1.x, x1.y), x1h = make_float2(x1.z, x1.w);
 #pragma unroll
               for (int q = 0; q < QG; ++q) {
                 const float2 ww = make_float2(wT[t][q], wT[t][q]);
-                a[0][q] = ffma2(xlo, ww, a[0][q]);
-                a[1][q] = ffma2(xhi, ww, a[1][q]);
+                a[0][0][q] = ffma2(x0l, ww, a[0][0][q]);
+                a[0][1][q] = ffma2(x0h, ww, a[0][1][q]);
+                a[1][0][q] = ffma2(x1l, ww, a[1][0][q]);
+                a[1][1][q] = ffma2(x1h, ww, a[1][1][q]);
               }
             }
 #pragma unroll
-            for (int q = 0; q < QG; ++q) {
-              const int qq = qg * QG + q;
-              if (qq < T)
-                *reinterpret_cast<float4*>(sY + sw_off(r0 + qq * V, c4)) = make_float4(a[0][q].x, a[0][q].y, a[1][q].x, a[1][q].y);
+            for (int h = 0; h < 2; ++h) {
+              float* yp = sY + (((wl * 4 + cp + h) * QG) * TTP + rem) * 4;
+#pragma unroll
+              for (int q = 0; q < QG; ++q)
+                if (qg * QG + q < T)
+                  *reinterpret_cast<float4*>(yp + q * TTP * 4) = make_float4(a[h][0][q].x, a[h][0][q].y, a[h][1][q].x, a[h][1][q].y);
             }
           }
         }
@@ -329,54 +352,68 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
     }
   } else if (warp < 8) {
     // =============================== A-mix warps ===============================
+    reg_inc<kRegsA>();
     // Y2[n,(t,w),c] = sum_v Y1[n,(t,v),c] * A[t][v][w]       stsgcn.py:155   (+ tf32 lo parts for the tensor pipe)
     const int atid = tid - kTcMix;
     const int ws = atid / Cfg::TA, rem = atid - ws * Cfg::TA;
-    const int t = rem / NWG, wg = rem - t * NWG;
-    const bool active = ws < Cfg::WS_A;
+    const int t = rem / NWG, wg = rem - t * NWG;  // thread wg of a frame owns output joints wg, wg+NWG, wg+2*NWG, ...
+    const bool active = ws < Cfg::WS_A;          // (so the NWG threads of a frame store consecutive operand rows)
     float wA[V][WGS];  // this thread's slice of the learned joint-mix matrix
 #pragma unroll
     for (int v = 0; v < V; ++v)
 #pragma unroll
       for (int j = 0; j < WGS; ++j)
-        wA[v][j] = (active && wg * WGS + j < V) ? __ldg(wt.A + (t * V + v) * VP + wg * WGS + j) : 0.f;
+        wA[v][j] = (active && wg + j * NWG < V) ? __ldg(wt.A + (t * V + v) * VP + wg + j * NWG) : 0.f;
 
     for (int it = 0; it < npairs; ++it) {
       const int b = it % NXB, s = it & 1;
       mbar_wait(BAR(BAR_Y1_FULL + s), uint32_t((it / 2) & 1));
       if (it >= 2) mbar_wait(BAR(BAR_MMA_DONE + s), uint32_t((it / 2 - 1) & 1));  // Y2[s], Y2lo[s] free again
       if (active) {
-        const float* sY = sY1 + s * ARR;
+        const float* sY = sY1 + s * Y1ARR;
         float* sZ = sY2 + s * ARR;
         float* sZlo = sY2lo + s * ARR;
         for (int wl = ws; wl < NW; wl += Cfg::WS_A) {
           const int r0 = wl * P + t * V;
 #pragma unroll 1
-          for (int c4 = 0; c4 < C4; ++c4) {
-            float2 a[2][WGS];
+          for (int cp = 0; cp < C4; cp += 2) {  // two 4-channel groups at once: two independent load streams
+            float2 a[2][2][WGS];
 #pragma unroll
-            for (int j = 0; j < WGS; ++j) a[0][j] = a[1][j] = make_float2(0.f, 0.f);
+            for (int j = 0; j < WGS; ++j) a[0][0][j] = a[0][1][j] = a[1][0][j] = a[1][1][j] = make_float2(0.f, 0.f);
+            const float* yp0 = sY + (((wl * 4 + cp) * QG + t % QG) * TTP + t / QG) * 4;  // element (v, t) at + v * NQG
+            const float* yp1 = yp0 + QG * TTP * 4;
+            float4 yn0 = *reinterpret_cast<const float4*>(yp0);
+            float4 yn1 = *reinterpret_cast<const float4*>(yp1);
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-              const float4 y = *reinterpret_cast<const float4*>(sY + sw_off(r0 + v, c4));
-              const float2 ylo = make_float2(y.x, y.y), yhi = make_float2(y.z, y.w);
+              const float4 y0 = yn0, y1 = yn1;
+              if (v + 1 < V) {  // next joint in flight
+                yn0 = *reinterpret_cast<const float4*>(yp0 + (v + 1) * NQG * 4);
+                yn1 = *reinterpret_cast<const float4*>(yp1 + (v + 1) * NQG * 4);
+              }
+              const float2 y0l = make_float2(y0.x, y0.y), y0h = make_float2(y0.z, y0.w);
+              const float2 y1l = make_float2(y1.x, y1.y), y1h = make_float2(y1.z, y1.w);
 #pragma unroll
               for (int j = 0; j < WGS; ++j) {
                 const float2 ww = make_float2(wA[v][j], wA[v][j]);
-                a[0][j] = ffma2(ylo, ww, a[0][j]);
-                a[1][j] = ffma2(yhi, ww, a[1][j]);
+                a[0][0][j] = ffma2(y0l, ww, a[0][0][j]);
+                a[0][1][j] = ffma2(y0h, ww, a[0][1][j]);
+                a[1][0][j] = ffma2(y1l, ww, a[1][0][j]);
+                a[1][1][j] = ffma2(y1h, ww, a[1][1][j]);
               }
             }
 #pragma unroll
-            for (int j = 0; j < WGS; ++j) {
-              const int w = wg * WGS + j;
-              if (w < V) {
-                const float4 o = make_float4(a[0][j].x, a[0][j].y, a[1][j].x, a[1][j].y);
-                const int off = sw_off(r0 + w, c4);
-                *reinterpret_cast<float4*>(sZ + off) = o;
-                *reinterpret_cast<float4*>(sZlo + off) = tf32_lo4(o);
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int j = 0; j < WGS; ++j) {
+                const int w = wg + j * NWG;
+                if (w < V) {
+                  const float4 o = make_float4(a[h][0][j].x, a[h][0][j].y, a[h][1][j].x, a[h][1][j].y);
+                  const int off = sw_off(r0 + w, cp + h);
+                  *reinterpret_cast<float4*>(sZ + off) = o;
+                  *reinterpret_cast<float4*>(sZlo + off) = tf32_lo4(o);
+                }
               }
-            }
           }
         }
       }
@@ -392,7 +429,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor pipe
       mbar_arrive(BAR(BAR_OPS_FULL + s));
     }
-  } else if (warp == kTcMmaWarp) {
+  } else if (warp >= kTcMmaWarp) {
+    reg_dec<kRegsS>();
+    if (warp == kTcMmaWarp) {
     // =============================== MMA-issuing warp ===============================
     const uint32_t idesc = umma_idesc_tf32(COUT);
     for (int it = 0; it < npairs; ++it) {
@@ -432,7 +471,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       }
       __syncwarp();
     }
-  } else if (warp == kTcLoadWarp) {
+    } else if (warp == kTcLoadWarp) {
     // =============================== loader warp ===============================
     const int64_t nrows = io.n * P;
     for (int it = 0; it < npairs; ++it) {
@@ -441,14 +480,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       const int b = it % NXB, s = it & 1;
       if (it >= NXB) mbar_wait(BAR(BAR_X_EMPTY + b), uint32_t((it / NXB - 1) & 1));
       {
-        float* dstb = sX + b * ARR;
+        // lane -> (row offset lane/4, 16-byte piece lane%4); 8 rows per warp step, swizzle phase repeats every 8 rows
+        const int j = lane & 3, rl = lane >> 2;
         const int64_t row0 = tile * ROWS;
-        const float* base = io.in + chunk * Cfg::KC;
-        for (int idx = lane; idx < ROWS * C4; idx += 32) {
-          const int r = idx >> 2, j = idx & 3;
-          const bool ok = (row0 + r) < nrows;
-          const float* src = ok ? base + (row0 + r) * CIN + j * 4 : io.in;
-          cp_async16(dstb + sw_off(r, j), src, ok);
+        int64_t left = nrows - row0 - rl;  // rows from this lane's first row to the end of the tensor
+        const float* src = io.in + (row0 + rl) * CIN + chunk * Cfg::KC + j * 4;
+        const uint32_t dst0 = smem_u32(sX + b * ARR) + uint32_t(rl * 64 + ((j ^ ((rl >> 1) & 3)) << 4));
+#pragma unroll 4
+        for (int r = 0; r < ROWS; r += 8) {
+          const bool ok = left > 0;
+          const int sz = ok ? 16 : 0;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst0 + uint32_t(r * 64)), "l"(ok ? src : io.in), "r"(sz) : "memory");
+          src += 8 * CIN;
+          left -= 8;
         }
         cp_async_mbar_arrive_noinc(BAR(BAR_X_FULL + b));
       }
@@ -460,11 +504,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       __syncwarp();
     }
     cp_async_wait_all();
+    }
   } else {
     // =============================== epilogue warps ===============================
+    reg_dec<kRegsE>();
     // TMEM -> bias, identity residual, PReLU, + Linear(SiLU(pos + cond)) -> channel-last store      stsgcn.py:109-114
     const float slope = wt.prelu;
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;  // TMEM lane quarter this warp may access (warps 8-11 -> quarters 0-3)
     const int etid = tid - kTcEpiWarp0 * 32;
     const int E = io.E;
     for (int ti = 0; ti < my_tiles; ++ti) {
