@@ -54,7 +54,7 @@ def workload_config(a):
             "windows_per_gpu_per_step": a.batch, "seg_len": a.seg_len, "T": T, "V": 17,
             "noise_steps": a.noise_steps, "n_generated_samples": a.gen,
             "window_steps_per_window": a.gen * (a.noise_steps - 1),
-            "cache": "per-step working set (activations of a >2000-window tile, ~0.9 GB) exceeds the 126 MB L2; "
+            "cache": "per-step working set (activations of a 9472-window tile, ~3.6 GB) exceeds the 126 MB L2; "
                      "fresh Philox noise every step"}
 
 

@@ -1026,7 +1026,7 @@ int mcd_score_windows_host(mcd_model* m, const float* h_data, int64_t B, int32_t
     m->host_best_floats = size_t(B);
   }
   const int64_t nv = int64_t(G) * B;
-  int64_t n_tile = tile_unit(m) * 16;
+  int64_t n_tile = tile_unit(m) * 64;
   if (n_tile > nv) n_tile = nv;
   const size_t need = carve_bytes(m, n_tile) + (align_floats(size_t(B) * m->E) + align_floats(size_t(nv))) * sizeof(float);
   if (need > m->host_ws_bytes) {

@@ -42,7 +42,7 @@ constexpr int kTcEpilogue = 128;
 constexpr int kTcLoadWarp = 13;    // the loader warp (warps 14-15 only pad the last warpgroup)
 constexpr int kTcThreads = 16 * 32;
 // Register budgets per warpgroup (setmaxnreg): the T-mix threads keep 96 weights + two accumulator sets in registers.
-constexpr int kRegsT = 184, kRegsA = 144, kRegsE = 112, kRegsS = 64;
+constexpr int kRegsT = 208, kRegsA = 168, kRegsE = 88, kRegsS = 48;
 static_assert(kRegsT + kRegsA + kRegsE + kRegsS <= 512, "one warp of each group shares an SM sub-partition (16K registers)");
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -128,6 +128,13 @@ __device__ __forceinline__ float4 ldg_nc4(const float* p) {  // read-only global
 }
 __device__ __forceinline__ void stg4(float* p, const float4 v) {
   asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// shared-memory 16-byte load the compiler will not sink towards its use (keeps the software pipeline's lead)
+__device__ __forceinline__ float4 lds4_early(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
 }
 
 // float index of (row r, 4-channel group c4) in a [rows][16] fp32 operand array laid out K-major SWIZZLE_64B
@@ -316,24 +323,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
             float2 a[2][2][QG];
 #pragma unroll
             for (int q = 0; q < QG; ++q) a[0][0][q] = a[0][1][q] = a[1][0][q] = a[1][1][q] = make_float2(0.f, 0.f);
-            float4 xn0 = *reinterpret_cast<const float4*>(sXc + sw_off(r0, cp));
-            float4 xn1 = *reinterpret_cast<const float4*>(sXc + sw_off(r0, cp + 1));
+            // software pipeline over blocks of TB frames: the 2*TB loads of the next block are issued before the
+            // 16*TB packed FMAs of the current one (one sub-partition hosts a single T-mix warp: nothing else hides
+            // the ~50-cycle shared-memory latency)
+            constexpr int TB = T % 3 == 0 ? 3 : (T % 2 == 0 ? 2 : 1);
+            float4 xc[TB][2], xn[TB][2];
 #pragma unroll
-            for (int t = 0; t < T; ++t) {
-              const float4 x0 = xn0, x1 = xn1;
-              if (t + 1 < T) {  // next frame in flight
-                xn0 = *reinterpret_cast<const float4*>(sXc + sw_off(r0 + (t + 1) * V, cp));
-                xn1 = *reinterpret_cast<const float4*>(sXc + sw_off(r0 + (t + 1) * V, cp + 1));
+            for (int i = 0; i < TB; ++i) {
+              xn[i][0] = lds4_early(sXc + sw_off(r0 + i * V, cp));
+              xn[i][1] = lds4_early(sXc + sw_off(r0 + i * V, cp + 1));
+            }
+#pragma unroll
+            for (int tb = 0; tb < T; tb += TB) {
+#pragma unroll
+              for (int i = 0; i < TB; ++i) { xc[i][0] = xn[i][0]; xc[i][1] = xn[i][1]; }
+              if (tb + TB < T) {
+#pragma unroll
+                for (int i = 0; i < TB; ++i) {
+                  xn[i][0] = lds4_early(sXc + sw_off(r0 + (tb + TB + i) * V, cp));
+                  xn[i][1] = lds4_early(sXc + sw_off(r0 + (tb + TB + i) * V, cp + 1));
+                }
               }
-              const float2 x0l = make_float2(x0.x, x0.y), x0h = make_float2(x0.z, x0.w);
-              const float2 x1l = make_float2(x1.x, x1.y), x1h = make_float2(x1.z, x1.w);
 #pragma unroll
-              for (int q = 0; q < QG; ++q) {
-                const float2 ww = make_float2(wT[t][q], wT[t][q]);
-                a[0][0][q] = ffma2(x0l, ww, a[0][0][q]);
-                a[0][1][q] = ffma2(x0h, ww, a[0][1][q]);
-                a[1][0][q] = ffma2(x1l, ww, a[1][0][q]);
-                a[1][1][q] = ffma2(x1h, ww, a[1][1][q]);
+              for (int i = 0; i < TB; ++i) {
+                const int t = tb + i;
+                const float2 x0l = make_float2(xc[i][0].x, xc[i][0].y), x0h = make_float2(xc[i][0].z, xc[i][0].w);
+                const float2 x1l = make_float2(xc[i][1].x, xc[i][1].y), x1h = make_float2(xc[i][1].z, xc[i][1].w);
+#pragma unroll
+                for (int q = 0; q < QG; ++q) {
+                  const float2 ww = make_float2(wT[t][q], wT[t][q]);
+                  a[0][0][q] = ffma2(x0l, ww, a[0][0][q]);
+                  a[0][1][q] = ffma2(x0h, ww, a[0][1][q]);
+                  a[1][0][q] = ffma2(x1l, ww, a[1][0][q]);
+                  a[1][1][q] = ffma2(x1h, ww, a[1][1][q]);
+                }
               }
             }
 #pragma unroll
@@ -382,24 +405,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
             for (int j = 0; j < WGS; ++j) a[0][0][j] = a[0][1][j] = a[1][0][j] = a[1][1][j] = make_float2(0.f, 0.f);
             const float* yp0 = sY + (((wl * 4 + cp) * QG + t % QG) * TTP + t / QG) * 4;  // element (v, t) at + v * NQG
             const float* yp1 = yp0 + QG * TTP * 4;
-            float4 yn0 = *reinterpret_cast<const float4*>(yp0);
-            float4 yn1 = *reinterpret_cast<const float4*>(yp1);
+            constexpr int VB = 3;  // joints per pipeline block (the last block may be partial)
+            float4 yc[VB][2], yn[VB][2];
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-              const float4 y0 = yn0, y1 = yn1;
-              if (v + 1 < V) {  // next joint in flight
-                yn0 = *reinterpret_cast<const float4*>(yp0 + (v + 1) * NQG * 4);
-                yn1 = *reinterpret_cast<const float4*>(yp1 + (v + 1) * NQG * 4);
+            for (int i = 0; i < VB; ++i)
+              if (i < V) {
+                yn[i][0] = lds4_early(yp0 + i * NQG * 4);
+                yn[i][1] = lds4_early(yp1 + i * NQG * 4);
               }
-              const float2 y0l = make_float2(y0.x, y0.y), y0h = make_float2(y0.z, y0.w);
-              const float2 y1l = make_float2(y1.x, y1.y), y1h = make_float2(y1.z, y1.w);
 #pragma unroll
-              for (int j = 0; j < WGS; ++j) {
-                const float2 ww = make_float2(wA[v][j], wA[v][j]);
-                a[0][0][j] = ffma2(y0l, ww, a[0][0][j]);
-                a[0][1][j] = ffma2(y0h, ww, a[0][1][j]);
-                a[1][0][j] = ffma2(y1l, ww, a[1][0][j]);
-                a[1][1][j] = ffma2(y1h, ww, a[1][1][j]);
+            for (int vb = 0; vb < V; vb += VB) {
+#pragma unroll
+              for (int i = 0; i < VB; ++i) { yc[i][0] = yn[i][0]; yc[i][1] = yn[i][1]; }
+#pragma unroll
+              for (int i = 0; i < VB; ++i)
+                if (vb + VB + i < V) {
+                  yn[i][0] = lds4_early(yp0 + (vb + VB + i) * NQG * 4);
+                  yn[i][1] = lds4_early(yp1 + (vb + VB + i) * NQG * 4);
+                }
+#pragma unroll
+              for (int i = 0; i < VB; ++i) {
+                const int v = vb + i;
+                if (v < V) {
+                  const float2 y0l = make_float2(yc[i][0].x, yc[i][0].y), y0h = make_float2(yc[i][0].z, yc[i][0].w);
+                  const float2 y1l = make_float2(yc[i][1].x, yc[i][1].y), y1h = make_float2(yc[i][1].z, yc[i][1].w);
+#pragma unroll
+                  for (int j = 0; j < WGS; ++j) {
+                    const float2 ww = make_float2(wA[v][j], wA[v][j]);
+                    a[0][0][j] = ffma2(y0l, ww, a[0][0][j]);
+                    a[0][1][j] = ffma2(y0h, ww, a[0][1][j]);
+                    a[1][0][j] = ffma2(y1l, ww, a[1][0][j]);
+                    a[1][1][j] = ffma2(y1h, ww, a[1][1][j]);
+                  }
+                }
               }
             }
 #pragma unroll
