@@ -166,6 +166,9 @@ MCD_API int mcd_score_windows_host(mcd_model* m, const float* h_data, int64_t B,
 /* ---- measurement support -------------------------------------------------------------------- */
 /* Number of kernel launches issued through this handle so far (bench.py's gpu_launches). */
 MCD_API int64_t mcd_launch_count(const mcd_model* m);
+/* Debug: arm a device-side timeline for the next launch of denoiser block `slot` (0..10): CTA 0 appends up to `cap`
+ * records of 4 x int64 (warp role, pair index, event id, clock64) to d_records.  Tensor-core block kernels only. */
+MCD_API int mcd_debug_trace_next(mcd_model* m, int slot, long long* d_records, int cap);
 /* Per-kernel device timing: when enabled every launch through this handle is bracketed by CUDA
  * events on its stream.  mcd_profile_read synchronises the device, adds the elapsed times into
  * per-kernel totals and returns them: for kernel slot i (0 <= i < mcd_profile_slots()),

@@ -61,6 +61,7 @@ SIGNATURES = {
     "mcd_score_windows_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_int64,
                                          C.c_void_p]),
     "mcd_launch_count": (C.c_int64, [C.c_void_p]),
+    "mcd_debug_trace_next": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "mcd_profile_slots": (C.c_int, []),
     "mcd_profile_slot_name": (C.c_char_p, [C.c_int]),
     "mcd_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),

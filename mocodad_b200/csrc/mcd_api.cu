@@ -117,6 +117,8 @@ struct mcd_model {
   size_t ws_buf = 0, ws_d1 = 0, ws_d2 = 0, ws_x = 0;
   // measurement
   mutable std::atomic<int64_t> launches{0};
+  mutable long long* d_trace = nullptr;  // debug timeline target for the next tensor-core block launch of slot trace_slot
+  mutable int trace_slot = -1, trace_cap = 0;
   mutable bool prof_on = false;
   mutable std::vector<ProfEvent> prof_events;
   mutable size_t prof_used = 0;
@@ -213,9 +215,11 @@ int dense_block_op(int action, const mcd_model* m, int slot, const BlockWeights*
   if (io->n <= 0) return MCD_OK;
   const int64_t ntiles = (io->n + Tc::NW - 1) / Tc::NW;
   const int grid = int(ntiles < m->num_sms ? ntiles : m->num_sms);
+  BlockIO io2 = *io;
+  if (m->d_trace != nullptr && m->trace_slot == slot) { io2.trace = m->d_trace; io2.trace_cap = m->trace_cap; m->trace_slot = -1; }
   {
     LaunchScope ls(m, slot, io->n, s);
-    stgcn_block_tc_kernel<Tc><<<grid, kTcThreads, Tc::SMEM_BYTES, s>>>(*w, *io);
+    stgcn_block_tc_kernel<Tc><<<grid, kTcThreads, Tc::SMEM_BYTES, s>>>(*w, io2);
   }
   return check_launch(kSlotNames[slot]);
 }
@@ -296,12 +300,13 @@ int launch_resample(const mcd_model* m, int idx, const float* in, const float* s
   const PackedResample& r = m->rs[idx];
   const int64_t frames = n * m->T;
   const int grid = grid_for(frames * (C / 4), kThreads, m->num_sms, 8);
+  const int T = m->T;
   {
     LaunchScope ls(m, SLOT_RS0 + idx, n, s);
-    if (r.vin == 17 && r.vout == 12) joint_resample_kernel<17, 12><<<grid, kThreads, 0, s>>>(in, skip, out, r.W, r.b, frames, C);
-    else if (r.vin == 12 && r.vout == 10) joint_resample_kernel<12, 10><<<grid, kThreads, 0, s>>>(in, skip, out, r.W, r.b, frames, C);
-    else if (r.vin == 10 && r.vout == 12) joint_resample_kernel<10, 12><<<grid, kThreads, 0, s>>>(in, skip, out, r.W, r.b, frames, C);
-    else if (r.vin == 12 && r.vout == 17) joint_resample_kernel<12, 17><<<grid, kThreads, 0, s>>>(in, skip, out, r.W, r.b, frames, C);
+    if (r.vin == 17 && r.vout == 12) joint_resample_kernel<17, 12><<<grid, kThreads, 0, s>>>(in, skip, out, r.W, r.b, n, T, C);
+    else if (r.vin == 12 && r.vout == 10) joint_resample_kernel<12, 10><<<grid, kThreads, 0, s>>>(in, skip, out, r.W, r.b, n, T, C);
+    else if (r.vin == 10 && r.vout == 12) joint_resample_kernel<10, 12><<<grid, kThreads, 0, s>>>(in, skip, out, r.W, r.b, n, T, C);
+    else if (r.vin == 12 && r.vout == 17) joint_resample_kernel<12, 17><<<grid, kThreads, 0, s>>>(in, skip, out, r.W, r.b, n, T, C);
     else return fail(MCD_ERR_UNSUPPORTED, "joint resample %d->%d", r.vin, r.vout);
   }
   return check_launch(kResample[idx].name);
@@ -815,7 +820,7 @@ int mcd_model_finalize(mcd_model* m) {
       snprintf(p, sizeof(p), "condition_encoder.encoder.model_layers.%d.", i);
       ok = pack_block(m, &ar, p, chans[i], chans[i + 1], m->Tc, 17, false, m->E, &m->enc[i], &eo[i], &missing) && ok;
     }
-    // models/stsae/stsae.py:87 flattens [C,T,V] row-major; our activations are [P][C]
+    // models/stsae/stsae.py:87 flattens [C,T,V] row-major; our activations are planar-4 [C/4][P][4]
     const int C = m->cfg.cond_h_dim, P = m->Tc * 17, K = C * P, L = m->E;
     auto* W = find(m, "condition_encoder.btlnk.weight", size_t(L) * K, &missing);
     auto* b = find(m, "condition_encoder.btlnk.bias", L, &missing);
@@ -824,7 +829,8 @@ int mcd_model_finalize(mcd_model* m) {
       btlb = ar.alloc(L);
       for (int c = 0; c < C; ++c)
         for (int p = 0; p < P; ++p)
-          for (int l = 0; l < L; ++l) ar.h[btlW + (size_t(p) * C + c) * L + l] = (*W)[size_t(l) * K + size_t(c) * P + p];
+          for (int l = 0; l < L; ++l)
+            ar.h[btlW + ((size_t(c / 4) * P + p) * 4 + c % 4) * L + l] = (*W)[size_t(l) * K + size_t(c) * P + p];
       for (int l = 0; l < L; ++l) ar.h[btlb + l] = (*b)[l];
     } else {
       ok = false;
@@ -1045,6 +1051,16 @@ int mcd_score_windows_host(mcd_model* m, const float* h_data, int64_t B, int32_t
 }
 
 int64_t mcd_launch_count(const mcd_model* m) { return m ? m->launches.load() : 0; }
+
+// Debug: arm a device-side timeline for the next launch of U-Net block `slot` (0..10); CTA 0 writes up to `cap`
+// records of 4 x int64 (role, pair, event, clock64) into d_records (zero-filled by the caller).
+int mcd_debug_trace_next(mcd_model* m, int slot, long long* d_records, int cap) {
+  if (m == nullptr) return fail(MCD_ERR_INVALID_ARG, "model handle is NULL");
+  m->d_trace = d_records;
+  m->trace_slot = slot;
+  m->trace_cap = cap;
+  return MCD_OK;
+}
 
 int mcd_profile_slots(void) { return SLOT_COUNT; }
 const char* mcd_profile_slot_name(int slot) { return (slot >= 0 && slot < SLOT_COUNT) ? kSlotNames[slot] : ""; }

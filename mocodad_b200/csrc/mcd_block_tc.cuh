@@ -3,7 +3,7 @@
 // make the contraction dense (Cin, Cout in {32, 64, 128}).
 //
 // Replaces ST_GCNN_layer.forward, models/gcae/stsgcn.py:94-116 (+ :143-156), like
-// stgcn_block_kernel in mcd_kernels.cuh, with the same HBM layout (channel-last [n][P][C] fp32).
+// stgcn_block_kernel in mcd_kernels.cuh, with the same HBM layout (planar-4 [n][C/4][P][4] fp32).
 //
 // Precision: the reference is fp32 and its DDPM chain amplifies denoiser errors ~200x,
 // so a plain TF32 product (10-bit mantissa) is not admissible.  Every fp32 operand x is split as
@@ -75,6 +75,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {  // one lane of the (converged) warp
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
 }
 // Bounded wait: a wedged pipeline traps (launch failure) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -265,6 +270,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
   const int npairs = my_tiles * NCHUNK;
   const uint32_t bar0 = smem_u32(&bars[0]);
   auto BAR = [&](int slot) { return bar0 + uint32_t(slot) * 8u; };
+  // debug timeline (mcd_debug_trace): lane 0 of each role's first warp in CTA 0 appends (role, pair, event, clock)
+  __shared__ int trace_n;
+  if (tid == 0) trace_n = 0;
+  auto TRACE = [&](int role, int it, int ev) {
+    if (io.trace != nullptr && blockIdx.x == 0 && lane == 0) {
+      const int k = atomicAdd(&trace_n, 1);
+      if (k < io.trace_cap) {
+        io.trace[4 * k + 0] = role; io.trace[4 * k + 1] = it; io.trace[4 * k + 2] = ev; io.trace[4 * k + 3] = clock64();
+      }
+    }
+  };
 
   // ---- once per CTA ----
   if (warp == kTcMmaWarp) {
@@ -311,8 +327,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
 
     for (int it = 0; it < npairs; ++it) {
       const int b = it % NXB, s = it & 1;
+      if (warp == 0) TRACE(0, it, 0);
       mbar_wait(BAR(BAR_X_FULL + b), uint32_t((it / NXB) & 1));
+      if (warp == 0) TRACE(0, it, 1);
       if (it >= 2) mbar_wait(BAR(BAR_Y1_EMPTY + s), uint32_t((it / 2 - 1) & 1));
+      if (warp == 0) TRACE(0, it, 2);
       if (active) {
         const float* sXc = sX + b * ARR;
         float* sY = sY1 + s * Y1ARR;
@@ -370,6 +389,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
           }
         }
       }
+      if (warp == 0) TRACE(0, it, 3);
       mbar_arrive(BAR(BAR_Y1_FULL + s));
       mbar_arrive(BAR(BAR_X_EMPTY + b));
     }
@@ -390,8 +410,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
 
     for (int it = 0; it < npairs; ++it) {
       const int b = it % NXB, s = it & 1;
+      if (warp == 4) TRACE(1, it, 0);
       mbar_wait(BAR(BAR_Y1_FULL + s), uint32_t((it / 2) & 1));
+      if (warp == 4) TRACE(1, it, 1);
       if (it >= 2) mbar_wait(BAR(BAR_MMA_DONE + s), uint32_t((it / 2 - 1) & 1));  // Y2[s], Y2lo[s] free again
+      if (warp == 4) TRACE(1, it, 2);
       if (active) {
         const float* sY = sY1 + s * Y1ARR;
         float* sZ = sY2 + s * ARR;
@@ -455,6 +478,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
           }
         }
       }
+      if (warp == 4) TRACE(1, it, 3);
       mbar_arrive(BAR(BAR_Y1_EMPTY + s));
       if constexpr (RESCONV) {  // lo part of X for the residual convolution (elementwise: the layouts coincide)
         mbar_wait(BAR(BAR_X_FULL + b), uint32_t((it / NXB) & 1));
@@ -465,6 +489,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
         mbar_arrive(BAR(BAR_X_EMPTY + b));
       }
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor pipe
+      if (warp == 4) TRACE(1, it, 4);
       mbar_arrive(BAR(BAR_OPS_FULL + s));
     }
   } else if (warp >= kTcMmaWarp) {
@@ -472,34 +497,42 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
     if (warp == kTcMmaWarp) {
     // =============================== MMA-issuing warp ===============================
     const uint32_t idesc = umma_idesc_tf32(COUT);
+    // operand descriptors of every buffer, computed once (warp-uniform): inside the loop a descriptor is base + constant
+    const uint64_t dY2_0 = umma_desc_sw64(smem_u32(sY2)), dY2_1 = umma_desc_sw64(smem_u32(sY2 + ARR));
+    const uint64_t dY2lo_0 = umma_desc_sw64(smem_u32(sY2lo)), dY2lo_1 = umma_desc_sw64(smem_u32(sY2lo + ARR));
+    const uint64_t dW_0 = umma_desc_sw64(smem_u32(sWc)), dW_1 = umma_desc_sw64(smem_u32(sWc + WCH));
+    const uint64_t dXlo = umma_desc_sw64(smem_u32(sXlo));
+    const uint64_t dX_0 = umma_desc_sw64(smem_u32(sX)), dX_1 = umma_desc_sw64(smem_u32(sX + ARR)),
+                   dX_2 = umma_desc_sw64(smem_u32(sX + (NXB > 2 ? 2 : 0) * ARR));
+    constexpr uint64_t PART = (COUT * 64) >> 4;  // one weight part, in descriptor address units (16 bytes)
     for (int it = 0; it < npairs; ++it) {
       const int ti = it / NCHUNK, chunk = it - ti * NCHUNK;
       const int set = ti & 1, s = it & 1, b = it % NXB;
+      TRACE(2, it, 0);
       mbar_wait(BAR(BAR_OPS_FULL + s), uint32_t((it / 2) & 1));
+      TRACE(2, it, 1);
       mbar_wait(BAR(BAR_W_FULL + s), uint32_t((it / 2) & 1));
+      TRACE(2, it, 2);
       if (chunk == 0 && ti >= 2) mbar_wait(BAR(BAR_ACC_EMPTY + set), uint32_t((ti / 2 - 1) & 1));  // set drained by the epilogue
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t aY2 = smem_u32(sY2 + s * ARR), aY2lo = smem_u32(sY2lo + s * ARR);
-        const uint32_t aX = smem_u32(sX + b * ARR), aXlo = smem_u32(sXlo);
-        const uint32_t bW = smem_u32(sWc + s * WCH);
-        constexpr uint32_t PART = COUT * 64;  // bytes per weight part
+      const uint64_t aHi = s ? dY2_1 : dY2_0, aLo = s ? dY2lo_1 : dY2lo_0, bW = s ? dW_1 : dW_0;
+      const uint64_t xHi = b == 0 ? dX_0 : (b == 1 ? dX_1 : dX_2);
+      const uint32_t d0 = tmem + set * Cfg::ACC_COLS;
+      const uint32_t acc0 = chunk > 0 ? 1u : 0u;
+      if (elect_one()) {
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
-          const uint32_t d = tmem + set * Cfg::ACC_COLS + m * COUT;
-          const uint32_t moff = m * 128 * 64;
-          uint32_t acc = chunk > 0 ? 1u : 0u;
+          const uint32_t d = d0 + m * COUT;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {  // two K=8 steps per 64-byte operand row
-            const uint32_t ko = h * 32;
-            umma_tf32(d, umma_desc_sw64(aY2lo + moff + ko), umma_desc_sw64(bW + ko), idesc, acc);
-            umma_tf32(d, umma_desc_sw64(aY2 + moff + ko), umma_desc_sw64(bW + PART + ko), idesc, 1u);
-            umma_tf32(d, umma_desc_sw64(aY2 + moff + ko), umma_desc_sw64(bW + ko), idesc, 1u);
-            acc = 1u;
+            const uint64_t ao = uint64_t((m * 128 * 64 + h * 32) >> 4), bo = uint64_t((h * 32) >> 4);
+            umma_tf32(d, aLo + ao, bW + bo, idesc, h == 0 ? acc0 : 1u);
+            umma_tf32(d, aHi + ao, bW + PART + bo, idesc, 1u);
+            umma_tf32(d, aHi + ao, bW + bo, idesc, 1u);
             if constexpr (RESCONV) {
-              umma_tf32(d, umma_desc_sw64(aXlo + moff + ko), umma_desc_sw64(bW + 2 * PART + ko), idesc, 1u);
-              umma_tf32(d, umma_desc_sw64(aX + moff + ko), umma_desc_sw64(bW + 3 * PART + ko), idesc, 1u);
-              umma_tf32(d, umma_desc_sw64(aX + moff + ko), umma_desc_sw64(bW + 2 * PART + ko), idesc, 1u);
+              umma_tf32(d, dXlo + ao, bW + 2 * PART + bo, idesc, 1u);
+              umma_tf32(d, xHi + ao, bW + 3 * PART + bo, idesc, 1u);
+              umma_tf32(d, xHi + ao, bW + 2 * PART + bo, idesc, 1u);
             }
           }
         }
@@ -508,33 +541,44 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
         if (chunk == NCHUNK - 1) umma_commit(BAR(BAR_ACC_FULL + set));  // the tile's accumulators are complete
       }
       __syncwarp();
+      TRACE(2, it, 3);
     }
     } else if (warp == kTcLoadWarp) {
     // =============================== loader warp ===============================
-    const int64_t nrows = io.n * P;
     for (int it = 0; it < npairs; ++it) {
       const int ti = it / NCHUNK, chunk = it - ti * NCHUNK;
       const int64_t tile = blockIdx.x + int64_t(ti) * gridDim.x;
       const int b = it % NXB, s = it & 1;
+      TRACE(3, it, 0);
       if (it >= NXB) mbar_wait(BAR(BAR_X_EMPTY + b), uint32_t((it / NXB - 1) & 1));
+      TRACE(3, it, 1);
       {
-        // lane -> (row offset lane/4, 16-byte piece lane%4); 8 rows per warp step, swizzle phase repeats every 8 rows
-        const int j = lane & 3, rl = lane >> 2;
-        const int64_t row0 = tile * ROWS;
-        int64_t left = nrows - row0 - rl;  // rows from this lane's first row to the end of the tensor
-        const float* src = io.in + (row0 + rl) * CIN + chunk * Cfg::KC + j * 4;
+        // lane -> (4-channel plane j = lane/8, row offset rl = lane%8): 8 consecutive positions of a plane per quarter
+        // warp (128 contiguous bytes of the planar-4 source); the swizzle phase of the destination repeats every 8 rows
+        const int j = lane >> 3, rl = lane & 7;
+        int wl = rl / P, pp = rl - wl * P;
         const uint32_t dst0 = smem_u32(sX + b * ARR) + uint32_t(rl * 64 + ((j ^ ((rl >> 1) & 3)) << 4));
+        const int g = chunk * C4 + j;
+        int64_t w = tile * NW + wl;
+        const float* src = io.in + act_off(w, g, pp, CIN, P);  // advances 8 positions (32 floats) per step inside a window
 #pragma unroll 4
         for (int r = 0; r < ROWS; r += 8) {
-          const bool ok = left > 0;
+          const bool ok = w < io.n;
           const int sz = ok ? 16 : 0;
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst0 + uint32_t(r * 64)), "l"(ok ? src : io.in), "r"(sz) : "memory");
-          src += 8 * CIN;
-          left -= 8;
+          pp += 8;
+          src += 32;
+          if (NW > 1 && pp >= P) {  // next window of the tile: its planes start CIN*P floats further
+            pp -= P;
+            ++w;
+            src += int64_t(CIN - 4) * P;
+          }
         }
         cp_async_mbar_arrive_noinc(BAR(BAR_X_FULL + b));
       }
+      TRACE(3, it, 2);
       if (it >= 2) mbar_wait(BAR(BAR_MMA_DONE + s), uint32_t((it / 2 - 1) & 1));  // W[s] free again
+      TRACE(3, it, 3);
       if (lane == 0) {
         mbar_expect_tx(BAR(BAR_W_FULL + s), uint32_t(WCH * 4));
         bulk_g2s(smem_u32(sWc + s * WCH), wt.Bop + size_t(chunk) * WCH, uint32_t(WCH * 4), BAR(BAR_W_FULL + s));
@@ -570,7 +614,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
         sEmb[i] = e;
       }
       named_bar_sync(2, kTcEpilogue);
+      if (warp == kTcEpiWarp0) TRACE(4, ti, 0);
       mbar_wait(BAR(BAR_ACC_FULL + set), uint32_t((ti / 2) & 1));
+      if (warp == kTcEpiWarp0) TRACE(4, ti, 1);
       tc_fence_after();
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
@@ -579,18 +625,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
         const int64_t w = tile * NW + wl;
         const bool ok = (r < ROWS) && (w < io.n);
         const float* embp = sEmb + (ok ? wl : 0) * COUT;
-        const int64_t grow = tile * ROWS + r;
+        const int pp = r - wl * P;  // consecutive lanes -> consecutive positions: planar-4 loads / stores are contiguous
 #pragma unroll 1
         for (int c0 = 0; c0 < COUT; c0 += 32) {
           float4 xr[8];
           if constexpr (!RESCONV) {  // identity residual: issue the loads of this column group before touching TMEM
-            const float* src = io.in + (ok ? grow : 0) * CIN + c0;
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) xr[j4] = ldg_nc4(src + j4 * 4);
+            for (int j4 = 0; j4 < 8; ++j4) xr[j4] = ldg_nc4(io.in + (ok ? act_off(w, (c0 >> 2) + j4, pp, CIN, P) : 0));
           }
           uint32_t acc[32];
           tmem_ld32(tmem + (uint32_t(q * 32) << 16) + uint32_t(set * Cfg::ACC_COLS + m * COUT + c0), acc);
-          float* dst = io.out + grow * COUT + c0;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             float o[4];
@@ -603,11 +647,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
               v = v > 0.f ? v : slope * v;
               o[jj] = v + f4get(e4, jj);
             }
-            if (ok) stg4(dst + j4 * 4, make_float4(o[0], o[1], o[2], o[3]));
+            if (ok) stg4(io.out + act_off(w, (c0 >> 2) + j4, pp, COUT, P), make_float4(o[0], o[1], o[2], o[3]));
           }
         }
       }
       tc_fence_before();  // accumulator reads ordered before the release of the set
+      if (warp == kTcEpiWarp0) TRACE(4, ti, 2);
       mbar_arrive(BAR(BAR_ACC_EMPTY + set));
     }
   }

@@ -2,9 +2,10 @@
 //
 // Data layout in HBM
 //   external tensors (x, eps, noise, data) keep the reference layout  [n][C=2][T][V]  fp32;
-//   activations between denoiser blocks are CHANNEL-LAST              [n][P=T*V][C]   fp32,
-//   so that one (frame,joint) position is a contiguous C-vector: the 1x1 channel convolution
-//   reads it with 128-bit shared loads and both graph mixes are vectorised over channels.
+//   activations between denoiser blocks are "PLANAR-4"                [n][C/4][P=T*V][4] fp32:
+//   16-byte elements of 4 consecutive channels, positions contiguous inside a 4-channel plane.  Channels stay
+//   vectorised (the graph mixes and the 1x1 convolution work on float4 channel groups) while every warp-wide
+//   global access -- one position per lane -- is a contiguous 512-byte span, for loads and stores alike.
 //
 // Kernels (reference code each one replaces, paths relative to the reference checkout):
 //   stgcn_block_kernel   ST_GCNN_layer.forward, models/gcae/stsgcn.py:94-116 (+ :143-156):
@@ -37,6 +38,9 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src
   int sz = pred ? 4 : 0;
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem_src), "r"(sz) : "memory");
 }
+// offset (floats) of the 4-channel group g of position p of window w in a planar-4 activation tensor with C channels
+__device__ __forceinline__ int64_t act_off(int64_t w, int g, int p, int C, int P) { return ((w * (C >> 2) + g) * int64_t(P) + p) * 4; }
+
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
@@ -97,6 +101,8 @@ struct BlockIO {
   const float* cond;  // [condB][E] conditioning embedding (nullptr: none); window w uses row (w0+w) % condB
   int64_t condB;
   int64_t w0;         // virtual index of window 0 of this launch
+  long long* trace;   // debug: CTA 0 records (role, pair, event, clock64) quadruples here (nullptr: off)
+  int trace_cap;      // capacity in records
   int32_t E;
 };
 
@@ -151,13 +157,12 @@ template <class Cfg>
 __device__ __forceinline__ void block_prefetch(const BlockIO& io, float* sXbuf, int64_t tile, int chunk, int tid) {
   constexpr int ROWS = Cfg::ROWS, CP = Cfg::CP, C4 = Cfg::C4, P = Cfg::P;
   if constexpr (Cfg::INMODE == IN_CL) {
-    const int64_t row0 = tile * ROWS;
-    const int64_t nrows = io.n * P;
-    const float* base = io.in + chunk * Cfg::KC;
     for (int idx = tid; idx < ROWS * C4; idx += kThreads) {
-      int r = idx / C4, j = idx - r * C4;
-      bool ok = (row0 + r) < nrows;
-      const float* src = ok ? base + (row0 + r) * Cfg::CIN + j * 4 : io.in;
+      const int j = idx / ROWS, r = idx - j * ROWS;  // consecutive threads -> consecutive positions of one 4-channel plane
+      const int wl = r / P, pp = r - wl * P;
+      const int64_t w = tile * Cfg::NW + wl;
+      const bool ok = w < io.n;
+      const float* src = ok ? io.in + act_off(w, chunk * C4 + j, pp, Cfg::CIN, P) : io.in;
       cp_async16(sXbuf + r * CP + j * 4, src, ok);
     }
   } else {  // channel-first, CIN real channels (2), padded channels stay zero (set once at start)
@@ -420,22 +425,14 @@ __global__ void __launch_bounds__(kThreads, 1) stgcn_block_kernel(const BlockWei
             return v;
           };
           if constexpr (Cfg::OUTMODE == OUT_CL) {
-            float* dst = io.out + (tile * ROWS + r) * COUT;
-            if constexpr (TCO % 4 == 0) {
+            static_assert(Cfg::OUTMODE != OUT_CL || TCO % 4 == 0, "planar-4 output needs whole 4-channel groups");
+            const int pp = r - wl * P;
 #pragma unroll
-              for (int g = 0; g < TCO / 4; ++g) {
-                const int co0 = g * (NCG * 4) + cg * 4;
-                const float4 o = make_float4(finish(acc[i][g * 2].x, co0), finish(acc[i][g * 2].y, co0 + 1),
-                                             finish(acc[i][g * 2 + 1].x, co0 + 2), finish(acc[i][g * 2 + 1].y, co0 + 3));
-                if (ok) *reinterpret_cast<float4*>(dst + co0) = o;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < TCO2; ++j) {
-                const int co0 = cg * TCO + j * 2;
-                const float2 o = make_float2(finish(acc[i][j].x, co0), finish(acc[i][j].y, co0 + 1));
-                if (ok) *reinterpret_cast<float2*>(dst + co0) = o;
-              }
+            for (int g = 0; g < TCO / 4; ++g) {
+              const int co0 = g * (NCG * 4) + cg * 4;
+              const float4 o = make_float4(finish(acc[i][g * 2].x, co0), finish(acc[i][g * 2].y, co0 + 1),
+                                           finish(acc[i][g * 2 + 1].x, co0 + 2), finish(acc[i][g * 2 + 1].y, co0 + 3));
+              if (ok) *reinterpret_cast<float4*>(io.out + act_off(w, co0 >> 2, pp, COUT, P)) = o;
             }
           } else {  // OUT_EPS: reference layout [n][COUT][P], plus the U-Net's outer residual +X
             static_assert(Cfg::OUTMODE == OUT_CL || TCO == 2, "OUT_EPS is the 2-channel output block");
@@ -472,24 +469,24 @@ __global__ void __launch_bounds__(kThreads) joint_resample_kernel(const float* _
                                                                    float* __restrict__ out,
                                                                    const float* __restrict__ Wd,  // [VOUT][VIN]
                                                                    const float* __restrict__ bd,  // [VOUT]
-                                                                   int64_t n_frames_total,        // n * T
-                                                                   int C) {
+                                                                   int64_t n, int T, int C) {
   __shared__ float sWd[VOUT * VIN];
   __shared__ float sb[VOUT];
   for (int i = threadIdx.x; i < VOUT * VIN; i += kThreads) sWd[i] = Wd[i];
   for (int i = threadIdx.x; i < VOUT; i += kThreads) sb[i] = bd[i];
   __syncthreads();
+  // one thread per (window, 4-channel plane, frame): planar-4 tensors keep a frame's joints contiguous (16 B apart)
   const int c4n = C / 4;
-  const int64_t total = n_frames_total * c4n;
+  const int64_t total = n * c4n * T;
   for (int64_t idx = blockIdx.x * int64_t(kThreads) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * kThreads) {
-    const int64_t f = idx / c4n;
-    const int c4 = int(idx - f * c4n);
-    const float* ip = in + (f * VIN) * C + c4 * 4;
+    const int64_t wg = idx / T;  // (window, plane)
+    const int t = int(idx - wg * T);
+    const float* ip = in + (wg * T + t) * int64_t(VIN) * 4;
     float4 x[VIN];
 #pragma unroll
-    for (int v = 0; v < VIN; ++v) x[v] = *reinterpret_cast<const float4*>(ip + int64_t(v) * C);
-    float* op = out + (f * VOUT) * C + c4 * 4;
-    const float* sp = skip ? skip + (f * VOUT) * C + c4 * 4 : nullptr;
+    for (int v = 0; v < VIN; ++v) x[v] = *reinterpret_cast<const float4*>(ip + v * 4);
+    float* op = out + (wg * T + t) * int64_t(VOUT) * 4;
+    const float* sp = skip ? skip + (wg * T + t) * int64_t(VOUT) * 4 : nullptr;
 #pragma unroll
     for (int w = 0; w < VOUT; ++w) {
       float4 a = make_float4(sb[w], sb[w], sb[w], sb[w]);
@@ -500,17 +497,17 @@ __global__ void __launch_bounds__(kThreads) joint_resample_kernel(const float* _
         a.z = fmaf(k, x[v].z, a.z); a.w = fmaf(k, x[v].w, a.w);
       }
       if (sp) {
-        const float4 s = *reinterpret_cast<const float4*>(sp + int64_t(w) * C);
-        a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w;
+        const float4 sv = *reinterpret_cast<const float4*>(sp + w * 4);
+        a.x += sv.x; a.y += sv.y; a.z += sv.z; a.w += sv.w;
       }
-      *reinterpret_cast<float4*>(op + int64_t(w) * C) = a;
+      *reinterpret_cast<float4*>(op + w * 4) = a;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // Bottleneck linear of the conditioning encoder: emb[n][l] = b[l] + sum_k h[n][k] * Wb[k][l]
-// h is channel-last [n][P*C]; Wb was re-indexed at pack time to that order.  One warp / window.
+// h is planar-4 [n][C/4][P][4]; Wb was re-indexed at pack time to that order.  One warp / window.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) bottleneck_kernel(const float* __restrict__ h, const float* __restrict__ Wb,
                                                               const float* __restrict__ bb, float* __restrict__ out,
@@ -648,7 +645,7 @@ __global__ void __launch_bounds__(kThreads) best_worst_kernel(const float* __res
   if (worst) worst[b] = hi;
 }
 
-// channel-last [n][P][C] -> reference layout [n][C][P]  (parity taps only)
+// planar-4 [n][C/4][P][4] -> reference layout [n][C][P]  (parity taps only)
 __global__ void __launch_bounds__(kThreads) cl_to_cf_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                             int64_t n, int P, int C) {
   const int64_t total = n * P * C;
@@ -656,7 +653,7 @@ __global__ void __launch_bounds__(kThreads) cl_to_cf_kernel(const float* __restr
     const int64_t w = i / (int64_t(P) * C);
     const int rem = int(i - w * P * C);
     const int c = rem / P, p = rem - c * P;
-    out[i] = in[(w * P + p) * C + c];
+    out[i] = in[act_off(w, c >> 2, p, C, P) + (c & 3)];
   }
 }
 
