@@ -15,8 +15,9 @@
 //
 // Structure of one CTA (persistent, one per SM), 4 warpgroups (register budgets re-balanced with setmaxnreg),
 // every hand-off through shared-memory mbarriers:
-//   warp 13     loader: cp.async of the next 16-channel activation chunk X (ring of 2-3 buffers) and one
-//               cp.async.bulk of the chunk's pre-swizzled weight operands;
+//   warp 13     loader: cp.async.bulk (TMA 1-D) copies of the next 16-channel activation chunk X -- one per
+//               (window, 4-channel plane), contiguous in the planar-4 source -- and of the chunk's pre-swizzled
+//               weight operands, completing on mbarriers;
 //   warps 0-3   T-mix  Y1[q,v,c] = sum_t X[t,v,c] T[v,t,q]: a thread owns (joint v, a group of output frames) and
 //               keeps its slice of the learned T matrix in REGISTERS for the whole launch, so the only shared
 //               traffic is one 16-byte activation read per 8 packed FMAs (the v2 kernel was shared-memory bound);
@@ -185,7 +186,7 @@ struct TcCfg {
   static constexpr int C4 = KC / 4;
   static constexpr bool RESCONV = CIN != COUT;
   static constexpr int NPART = RESCONV ? 4 : 2;  // weight operand parts per chunk: W hi, W lo [, Wr hi, Wr lo]
-  static constexpr int NXB = RESCONV ? 3 : 2;    // X ring depth (X is an MMA operand only with a residual convolution)
+  static constexpr int NXB = 2;                  // X ring depth (X lands planar: [window][c4][position] 16-byte elements)
   static constexpr int VP = (V + 3) / 4 * 4;
   static constexpr int TP4 = (T + 3) / 4 * 4;
   static constexpr int TMS = T * TP4 + 4;
@@ -214,8 +215,9 @@ struct TcCfg {
   static constexpr int WCH = NPART * COUT * 16;  // one chunk of weight operands
   static constexpr int SM_X = 0;                 // NXB buffers
   static constexpr int SM_Y1 = SM_X + NXB * ARR;  // 2
-  static constexpr int SM_XLO = SM_Y1 + 2 * Y1ARR;  // 1 (residual convolution only)
-  static constexpr int SM_Y2 = SM_XLO + (RESCONV ? ARR : 0);  // 2
+  static constexpr int SM_XHI = SM_Y1 + 2 * Y1ARR;              // 1: X in operand layout (residual convolution only)
+  static constexpr int SM_XLO = SM_XHI + (RESCONV ? ARR : 0);   // 1: its tf32 lo part
+  static constexpr int SM_Y2 = SM_XLO + (RESCONV ? ARR : 0);    // 2
   static constexpr int SM_Y2LO = SM_Y2 + 2 * ARR;             // 2
   static constexpr int SM_WC = SM_Y2LO + 2 * ARR;             // 2; also absorbs the last tile's over-read
   static constexpr int SM_BIAS = SM_WC + 2 * WCH;
@@ -253,6 +255,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
   float* smem = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   float* sX = smem + Cfg::SM_X;
   float* sY1 = smem + Cfg::SM_Y1;
+  float* sXhi = smem + Cfg::SM_XHI;
   float* sXlo = smem + Cfg::SM_XLO;
   float* sY2 = smem + Cfg::SM_Y2;
   float* sY2lo = smem + Cfg::SM_Y2LO;
@@ -290,8 +293,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   } else if (tid == 0) {
     for (int i = 0; i < 3; ++i) {
-      mbar_init(BAR(BAR_X_FULL + i), 32);
-      mbar_init(BAR(BAR_X_EMPTY + i), RESCONV ? 2 * kTcMix + 1 : kTcMix);
+      mbar_init(BAR(BAR_X_FULL + i), 1);  // one expect_tx arrival + the bulk copies' bytes
+      mbar_init(BAR(BAR_X_EMPTY + i), RESCONV ? 2 * kTcMix : kTcMix);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(BAR(BAR_W_FULL + i), 1);
@@ -336,7 +339,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
         const float* sXc = sX + b * ARR;
         float* sY = sY1 + s * Y1ARR;
         for (int wl = ws; wl < NW; wl += Cfg::WS_T) {
-          const int r0 = wl * P + v;
 #pragma unroll 1
           for (int cp = 0; cp < C4; cp += 2) {  // two 4-channel groups at once: two independent load streams
             float2 a[2][2][QG];
@@ -346,11 +348,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
             // 16*TB packed FMAs of the current one (one sub-partition hosts a single T-mix warp: nothing else hides
             // the ~50-cycle shared-memory latency)
             constexpr int TB = T % 3 == 0 ? 3 : (T % 2 == 0 ? 2 : 1);
+            const float* xp0 = sXc + ((wl * 4 + cp) * P + v) * 4;  // planar X: [window][c4][position] 16-byte elements
+            const float* xp1 = xp0 + P * 4;
             float4 xc[TB][2], xn[TB][2];
 #pragma unroll
             for (int i = 0; i < TB; ++i) {
-              xn[i][0] = lds4_early(sXc + sw_off(r0 + i * V, cp));
-              xn[i][1] = lds4_early(sXc + sw_off(r0 + i * V, cp + 1));
+              xn[i][0] = lds4_early(xp0 + i * V * 4);
+              xn[i][1] = lds4_early(xp1 + i * V * 4);
             }
 #pragma unroll
             for (int tb = 0; tb < T; tb += TB) {
@@ -359,8 +363,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
               if (tb + TB < T) {
 #pragma unroll
                 for (int i = 0; i < TB; ++i) {
-                  xn[i][0] = lds4_early(sXc + sw_off(r0 + (tb + TB + i) * V, cp));
-                  xn[i][1] = lds4_early(sXc + sw_off(r0 + (tb + TB + i) * V, cp + 1));
+                  xn[i][0] = lds4_early(xp0 + (tb + TB + i) * V * 4);
+                  xn[i][1] = lds4_early(xp1 + (tb + TB + i) * V * 4);
                 }
               }
 #pragma unroll
@@ -399,7 +403,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
     // Y2[n,(t,w),c] = sum_v Y1[n,(t,v),c] * A[t][v][w]       stsgcn.py:155   (+ tf32 lo parts for the tensor pipe)
     const int atid = tid - kTcMix;
     const int ws = atid / Cfg::TA, rem = atid - ws * Cfg::TA;
-    const int t = rem / NWG, wg = rem - t * NWG;  // thread wg of a frame owns output joints wg, wg+NWG, wg+2*NWG, ...
+    // thread wg of a frame owns output joints wg, wg+NWG, ...; frames are dealt to consecutive thread groups with a
+    // stride FS coprime to T chosen so that the 8 lanes of a quarter warp store to 8 different bank groups
+    constexpr int FS = (V % 8 == 1 && T % 5 != 0) ? 5 : 1;
+    const int tk = rem / NWG, wg = rem - tk * NWG;
+    const int t = (tk * FS) % T;
     const bool active = ws < Cfg::WS_A;          // (so the NWG threads of a frame store consecutive operand rows)
     float wA[V][WGS];  // this thread's slice of the learned joint-mix matrix
 #pragma unroll
@@ -480,12 +488,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       }
       if (warp == 4) TRACE(1, it, 3);
       mbar_arrive(BAR(BAR_Y1_EMPTY + s));
-      if constexpr (RESCONV) {  // lo part of X for the residual convolution (elementwise: the layouts coincide)
+      if constexpr (RESCONV) {  // X and its tf32 lo part in operand layout for the residual convolution
         mbar_wait(BAR(BAR_X_FULL + b), uint32_t((it / NXB) & 1));
-        if (it >= 1) mbar_wait(BAR(BAR_MMA_DONE + ((it - 1) & 1)), uint32_t(((it - 1) / 2) & 1));  // single Xlo buffer
+        if (it >= 1) mbar_wait(BAR(BAR_MMA_DONE + ((it - 1) & 1)), uint32_t(((it - 1) / 2) & 1));  // single Xhi / Xlo buffer
         const float* sXc = sX + b * ARR;
-        for (int idx = atid; idx < ROWS * C4; idx += kTcMix)
-          *reinterpret_cast<float4*>(sXlo + idx * 4) = tf32_lo4(*reinterpret_cast<const float4*>(sXc + idx * 4));
+        for (int idx = atid; idx < ROWS * C4; idx += kTcMix) {
+          const int c4 = idx / ROWS, r = idx - c4 * ROWS;  // consecutive threads -> consecutive positions
+          const int wl = r / P, pp = r - wl * P;
+          const float4 x = *reinterpret_cast<const float4*>(sXc + ((wl * 4 + c4) * P + pp) * 4);
+          const int off = sw_off(r, c4);
+          *reinterpret_cast<float4*>(sXhi + off) = x;
+          *reinterpret_cast<float4*>(sXlo + off) = tf32_lo4(x);
+        }
         mbar_arrive(BAR(BAR_X_EMPTY + b));
       }
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor pipe
@@ -502,12 +516,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
     const uint64_t dY2lo_0 = umma_desc_sw64(smem_u32(sY2lo)), dY2lo_1 = umma_desc_sw64(smem_u32(sY2lo + ARR));
     const uint64_t dW_0 = umma_desc_sw64(smem_u32(sWc)), dW_1 = umma_desc_sw64(smem_u32(sWc + WCH));
     const uint64_t dXlo = umma_desc_sw64(smem_u32(sXlo));
-    const uint64_t dX_0 = umma_desc_sw64(smem_u32(sX)), dX_1 = umma_desc_sw64(smem_u32(sX + ARR)),
-                   dX_2 = umma_desc_sw64(smem_u32(sX + (NXB > 2 ? 2 : 0) * ARR));
+    const uint64_t xHi = umma_desc_sw64(smem_u32(sXhi));
     constexpr uint64_t PART = (COUT * 64) >> 4;  // one weight part, in descriptor address units (16 bytes)
     for (int it = 0; it < npairs; ++it) {
       const int ti = it / NCHUNK, chunk = it - ti * NCHUNK;
-      const int set = ti & 1, s = it & 1, b = it % NXB;
+      const int set = ti & 1, s = it & 1;
       TRACE(2, it, 0);
       mbar_wait(BAR(BAR_OPS_FULL + s), uint32_t((it / 2) & 1));
       TRACE(2, it, 1);
@@ -516,7 +529,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       if (chunk == 0 && ti >= 2) mbar_wait(BAR(BAR_ACC_EMPTY + set), uint32_t((ti / 2 - 1) & 1));  // set drained by the epilogue
       tc_fence_after();
       const uint64_t aHi = s ? dY2_1 : dY2_0, aLo = s ? dY2lo_1 : dY2lo_0, bW = s ? dW_1 : dW_0;
-      const uint64_t xHi = b == 0 ? dX_0 : (b == 1 ? dX_1 : dX_2);
       const uint32_t d0 = tmem + set * Cfg::ACC_COLS;
       const uint32_t acc0 = chunk > 0 ? 1u : 0u;
       if (elect_one()) {
@@ -537,7 +549,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
           }
         }
         umma_commit(BAR(BAR_MMA_DONE + s));
-        if constexpr (RESCONV) umma_commit(BAR(BAR_X_EMPTY + b));
         if (chunk == NCHUNK - 1) umma_commit(BAR(BAR_ACC_FULL + set));  // the tile's accumulators are complete
       }
       __syncwarp();
@@ -552,29 +563,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       TRACE(3, it, 0);
       if (it >= NXB) mbar_wait(BAR(BAR_X_EMPTY + b), uint32_t((it / NXB - 1) & 1));
       TRACE(3, it, 1);
-      {
-        // lane -> (4-channel plane j = lane/8, row offset rl = lane%8): 8 consecutive positions of a plane per quarter
-        // warp (128 contiguous bytes of the planar-4 source); the swizzle phase of the destination repeats every 8 rows
-        const int j = lane >> 3, rl = lane & 7;
-        int wl = rl / P, pp = rl - wl * P;
-        const uint32_t dst0 = smem_u32(sX + b * ARR) + uint32_t(rl * 64 + ((j ^ ((rl >> 1) & 3)) << 4));
-        const int g = chunk * C4 + j;
-        int64_t w = tile * NW + wl;
-        const float* src = io.in + act_off(w, g, pp, CIN, P);  // advances 8 positions (32 floats) per step inside a window
-#pragma unroll 4
-        for (int r = 0; r < ROWS; r += 8) {
-          const bool ok = w < io.n;
-          const int sz = ok ? 16 : 0;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst0 + uint32_t(r * 64)), "l"(ok ? src : io.in), "r"(sz) : "memory");
-          pp += 8;
-          src += 32;
-          if (NW > 1 && pp >= P) {  // next window of the tile: its planes start CIN*P floats further
-            pp -= P;
-            ++w;
-            src += int64_t(CIN - 4) * P;
-          }
-        }
-        cp_async_mbar_arrive_noinc(BAR(BAR_X_FULL + b));
+      if (lane == 0) {
+        // one bulk copy per (window, 4-channel plane): P x 16 contiguous bytes of the planar-4 source land as one
+        // plane of the planar X buffer; windows past the end of the tensor are skipped (their rows are never stored)
+        int64_t nvalid = io.n - tile * NW;
+        if (nvalid > NW) nvalid = NW;
+        constexpr uint32_t PLANE = P * 16;
+        mbar_expect_tx(BAR(BAR_X_FULL + b), uint32_t(nvalid) * 4u * PLANE);
+        const uint32_t dst0 = smem_u32(sX + b * ARR);
+        for (int wl = 0; wl < int(nvalid); ++wl)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            bulk_g2s(dst0 + uint32_t(wl * 4 + j) * PLANE, io.in + act_off(tile * NW + wl, chunk * C4 + j, 0, CIN, P), PLANE,
+                     BAR(BAR_X_FULL + b));
       }
       TRACE(3, it, 2);
       if (it >= 2) mbar_wait(BAR(BAR_MMA_DONE + s), uint32_t((it / 2 - 1) & 1));  // W[s] free again
@@ -585,7 +586,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       }
       __syncwarp();
     }
-    cp_async_wait_all();
     }
   } else {
     // =============================== epilogue warps ===============================
