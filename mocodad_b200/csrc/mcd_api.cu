@@ -6,6 +6,7 @@
 #include "../../include/mocodad_b200.h"
 #include "mcd_kernels.cuh"
 #include "mcd_block_tc.cuh"
+#include "mcd_edge_blocks.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -224,11 +225,27 @@ int dense_block_op(int action, const mcd_model* m, int slot, const BlockWeights*
   return check_launch(kSlotNames[slot]);
 }
 
+// The first / last block of the denoiser (2-channel side): mcd_edge_blocks.cuh
+template <int T, bool HEAD>
+int edge_block_op(int action, const mcd_model* m, int slot, const BlockWeights* w, const BlockIO* io, cudaStream_t s) {
+  using Cfg = EdgeCfg<T, 17, nw_for(T, 17), HEAD>;
+  if (action == 0) return MCD_OK;
+  if (io->n <= 0) return MCD_OK;
+  const int64_t ntiles = (io->n + Cfg::NW - 1) / Cfg::NW;
+  const int64_t cap = int64_t(m->num_sms) * 2;
+  const int grid = int(ntiles < cap ? ntiles : cap);
+  {
+    LaunchScope ls(m, slot, io->n, s);
+    edge_block_kernel<Cfg><<<grid, Cfg::THREADS, 0, s>>>(*w, *io);
+  }
+  return check_launch(kSlotNames[slot]);
+}
+
 template <int T>
 int unet_block_op(int action, int idx, const mcd_model* m, const BlockWeights* w, const BlockIO* io, cudaStream_t s) {
   const int slot = SLOT_UNET0 + idx;
   switch (idx) {
-    case 0: return block_op<T, 17, 2, 16, true, IN_CF, OUT_CL>(action, m, slot, w, io, s);
+    case 0: return edge_block_op<T, true>(action, m, slot, w, io, s);
     case 1: return block_op<T, 17, 16, 32, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
     case 2: return dense_block_op<T, 17, 32, 32>(action, m, slot, w, io, s);
     case 3: return dense_block_op<T, 12, 32, 64>(action, m, slot, w, io, s);
@@ -238,7 +255,7 @@ int unet_block_op(int action, int idx, const mcd_model* m, const BlockWeights* w
     case 7: return dense_block_op<T, 12, 64, 64>(action, m, slot, w, io, s);
     case 8: return dense_block_op<T, 12, 64, 32>(action, m, slot, w, io, s);
     case 9: return dense_block_op<T, 17, 32, 32>(action, m, slot, w, io, s);
-    case 10: return block_op<T, 17, 32, 2, true, IN_CL, OUT_EPS>(action, m, slot, w, io, s);
+    case 10: return edge_block_op<T, false>(action, m, slot, w, io, s);
   }
   return fail(MCD_ERR_INVALID_ARG, "bad U-Net block index %d", idx);
 }

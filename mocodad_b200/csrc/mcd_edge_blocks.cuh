@@ -1,0 +1,173 @@
+// mcd_edge_blocks.cuh -- the first (2 -> 16 channels) and last (32 -> 2 channels) ST-GCN blocks of the denoiser
+// (st_gcnnsp1a.0 and st_gcnnsu3.1; ST_GCNN_layer.forward, models/gcae/stsgcn.py:94-116).
+//
+// One side of these blocks has only the 2 coordinate channels.  The learned mixes act on positions, the 1x1
+// convolution on channels, both are linear, so they commute:  W (A∘T)(X) = (A∘T)(W X).  The mixes are therefore run
+// on the 2-channel side -- after the convolution in the last block, before it in the first -- which cuts their work
+// 16x (8x) and leaves kernels whose cost is reading / writing the wide side once (HBM-bound).  fp32 throughout; the
+// re-association changes results by rounding only (parity tests: 2e-5 against the reference per layer).
+//
+// One thread per (window of the tile, position (t, v)); the 2-channel planes pass through shared memory between
+// the T-mix and the A-mix; the mix matrices are read through the read-only L1 path.
+#pragma once
+#include "mcd_kernels.cuh"
+
+namespace mcd {
+
+template <int T_, int V_, int NW_, bool HEAD_>
+struct EdgeCfg {
+  static constexpr int T = T_, V = V_, NW = NW_;
+  static constexpr bool HEAD = HEAD_;
+  static constexpr int P = T * V;
+  static constexpr int ROWS = NW * P;
+  static constexpr int THREADS = (ROWS + 31) / 32 * 32;
+  static constexpr int CW = HEAD ? 16 : 32;  // channels of the wide side
+  static constexpr int CE = HEAD ? 16 : 2;   // output channels (embedding width)
+  static constexpr int VP = (V + 3) / 4 * 4;
+  static constexpr int TP4 = (T + 3) / 4 * 4;
+  static constexpr int TMS = T * TP4 + 4;
+  static_assert(THREADS <= 1024, "tile too large");
+};
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS) edge_block_kernel(const BlockWeights wt, const BlockIO io) {
+  constexpr int T = Cfg::T, V = Cfg::V, P = Cfg::P, ROWS = Cfg::ROWS, NW = Cfg::NW;
+  constexpr int VP = Cfg::VP, TP4 = Cfg::TP4, TMS = Cfg::TMS, CW = Cfg::CW, CE = Cfg::CE;
+  constexpr bool HEAD = Cfg::HEAD;
+  __shared__ float s0[2][ROWS];       // mix input  (2 channels)
+  __shared__ float s1[2][ROWS];       // after the T-mix
+  __shared__ float sEmb[NW][CE];      // Linear(SiLU(pos + cond)) of the tile's windows
+  __shared__ float sW[2][CW][2];      // TAIL: [conv | residual conv][k][c']   HEAD: [conv | residual conv][co][k]
+  __shared__ float sBias[CE];
+
+  const int tid = threadIdx.x;
+  // folded weights: Wt / Wrt are stored [k][cout] (k padded to 4 for the head)
+  for (int i = tid; i < 2 * CW * 2; i += Cfg::THREADS) {
+    const int which = i / (CW * 2), rem = i - which * CW * 2;
+    const float* src = which == 0 ? wt.Wt : wt.Wrt;
+    if constexpr (HEAD) {
+      const int co = rem / 2, k = rem - co * 2;
+      sW[which][co][k] = src[k * 16 + co];
+    } else {
+      const int k = rem / 2, c = rem - k * 2;
+      sW[which][k][c] = src[k * 2 + c];
+    }
+  }
+  for (int i = tid; i < CE; i += Cfg::THREADS) sBias[i] = wt.bias[i];
+  __syncthreads();
+
+  const int64_t ntiles = (io.n + NW - 1) / NW;
+  const bool live = tid < ROWS;
+  const int wl = live ? tid / P : 0;
+  const int p = tid - wl * P;
+  const int tq = p / V, vw = p - tq * V;  // this thread's (frame, joint)
+  const float slope = wt.prelu;
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t w = tile * NW + wl;
+    const bool ok = live && w < io.n;
+    float x0 = 0.f, x1 = 0.f;  // HEAD: the input coordinates; TAIL: the residual-convolution outputs
+    if (ok) {
+      if constexpr (HEAD) {
+        const float* src = io.in + w * io.in_sn + io.in_t0 * V + p;
+        x0 = __ldg(src);
+        x1 = __ldg(src + io.in_sc);
+        s0[0][tid] = x0;
+        s0[1][tid] = x1;
+      } else {
+        float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+        for (int g = 0; g < CW / 4; ++g) {
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(io.in + act_off(w, g, p, CW, P)));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const float xk = f4get(xv, kk);
+            const int k = g * 4 + kk;
+            u0 = fmaf(sW[0][k][0], xk, u0);
+            u1 = fmaf(sW[0][k][1], xk, u1);
+            x0 = fmaf(sW[1][k][0], xk, x0);
+            x1 = fmaf(sW[1][k][1], xk, x1);
+          }
+        }
+        s0[0][tid] = u0;
+        s0[1][tid] = u1;
+      }
+    } else if (live) {
+      s0[0][tid] = 0.f;
+      s0[1][tid] = 0.f;
+    }
+    // time/condition embedding of the tile's windows (stsgcn.py:112-114)
+    for (int i = tid; i < NW * CE; i += Cfg::THREADS) {
+      const int ewl = i / CE, co = i - ewl * CE;
+      const int64_t ew = tile * NW + ewl;
+      float e = __ldg(wt.bE + co);
+      for (int j = 0; j < io.E; ++j) {
+        float v = __ldg(io.pos + j);
+        if (io.cond != nullptr && ew < io.n) v += __ldg(io.cond + ((io.w0 + ew) % io.condB) * io.E + j);
+        e = fmaf(__ldg(wt.WEt + j * CE + co), v / (1.0f + expf(-v)), e);
+      }
+      sEmb[ewl][co] = e;
+    }
+    __syncthreads();
+
+    // T-mix: y1[c][q][v] = sum_t s0[c][t][v] * Tm[v][t][q]      (this thread: q = tq, v = vw)        stsgcn.py:154
+    if (live) {
+      float a0 = 0.f, a1 = 0.f;
+      const float* tp = wt.Tm + vw * TMS + tq;
+      const int base = wl * P + vw;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const float k = __ldg(tp + t * TP4);
+        a0 = fmaf(s0[0][base + t * V], k, a0);
+        a1 = fmaf(s0[1][base + t * V], k, a1);
+      }
+      s1[0][tid] = a0;
+      s1[1][tid] = a1;
+    }
+    __syncthreads();
+
+    // A-mix: y2[c][t][w] = sum_v s1[c][t][v] * A[t][v][w]       (this thread: t = tq, w = vw)        stsgcn.py:155
+    if (live) {
+      float m0 = 0.f, m1 = 0.f;
+      const float* ap = wt.A + tq * V * VP + vw;
+      const int base = wl * P + tq * V;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float k = __ldg(ap + v * VP);
+        m0 = fmaf(s1[0][base + v], k, m0);
+        m1 = fmaf(s1[1][base + v], k, m1);
+      }
+      if (ok) {
+        if constexpr (HEAD) {  // 1x1 conv 2 -> 16 (+ residual conv), PReLU, + emb -> planar-4
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float o[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int co = g * 4 + jj;
+              float v = sBias[co];
+              v = fmaf(sW[0][co][0], m0, v);
+              v = fmaf(sW[0][co][1], m1, v);
+              v = fmaf(sW[1][co][0], x0, v);
+              v = fmaf(sW[1][co][1], x1, v);
+              v = v > 0.f ? v : slope * v;
+              o[jj] = v + sEmb[wl][co];
+            }
+            *reinterpret_cast<float4*>(io.out + act_off(w, g, p, 16, P)) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        } else {  // + residual conv, PReLU, + emb, + the U-Net's outer residual -> reference layout [n][2][P]
+          float v0 = m0 + x0 + sBias[0], v1 = m1 + x1 + sBias[1];
+          v0 = (v0 > 0.f ? v0 : slope * v0) + sEmb[wl][0];
+          v1 = (v1 > 0.f ? v1 : slope * v1) + sEmb[wl][1];
+          const int64_t e0 = (w * 2) * P + p;
+          if (io.xres != nullptr) { v0 += __ldg(io.xres + e0); v1 += __ldg(io.xres + e0 + P); }
+          io.out[e0] = v0;
+          io.out[e0 + P] = v1;
+        }
+      }
+    }
+    __syncthreads();  // s0 / sEmb are rewritten by the next tile
+  }
+}
+
+}  // namespace mcd
