@@ -167,6 +167,9 @@ def run_b200(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the single JSON line: NCCL's version banner goes to stdout at INFO/VERSION level
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO") and not os.environ.get("MCD_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -297,7 +300,7 @@ def run_b200(a):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": B * 4,
                     "ms_per_step": e2e_s * 1e3, "api": "mcd_score_windows_host (pinned host windows in, host scores out)"},
             "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "kernels": kernels[:8]}
+            "kernels": kernels[:10]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
