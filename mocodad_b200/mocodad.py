@@ -372,17 +372,18 @@ class MoCoDAD(_Base):
         return self.post_processing(out, gt_data, trans, meta, frames)
 
     def post_processing(self, out, gt_data, trans, meta, frames) -> float:
-        """Score assembly -> AUC (mocodad.py:337-430).  Host-side numpy/scipy/sklearn code that is
-        consumed unchanged from the reference tree: this method borrows the
-        reference's own function, so it needs the reference repo on sys.path."""
-        try:
-            from models.mocodad import MoCoDAD as _Ref  # the reference checkout
-        except Exception as e:  # pragma: no cover
-            raise RuntimeError("post_processing delegates to the reference's models/mocodad.py (host-side AUC code, "
-                               "out of this path's scope); put the reference checkout on sys.path") from e
-        if _Ref is MoCoDAD:
-            raise RuntimeError("models.mocodad resolves to this class; keep the reference's post_processing importable")
-        return _Ref.post_processing(self, out, gt_data, trans, meta, frames)
+        """Score assembly -> frame-level AUC (mocodad.py:337-430): per clip / person max over windows, padding around
+        absences, log-range mix over persons, HR masks, shift + Gaussian smoothing, mean over the affine
+        transformations, ``roc_auc_score``.  Host-side numpy (mocodad_b200/postproc.py), pinned against the reference."""
+        from . import postproc
+        gt = postproc.load_ground_truth(self.gt_path)
+        clip_masks = postproc.hr_ubnormal_masks(self.split) if (self.use_hr and self.dataset_name == 'UBnormal') else None
+        avenue = postproc.avenue_hr_mask() if self.dataset_name == 'HR-Avenue' else None
+        return float(postproc.dataset_auc(np.asarray(out), np.asarray(trans), np.asarray(meta), np.asarray(frames), gt,
+                                          num_transform=self.num_transforms, pad_size=self.anomaly_score_pad_size,
+                                          frames_shift=self.anomaly_score_frames_shift,
+                                          filter_kernel_size=self.anomaly_score_filter_kernel_size,
+                                          clip_masks=clip_masks, avenue_masks=avenue))
 
     def test_on_saved_tensors(self, split_name: str) -> float:
         """mocodad.py:433-448"""

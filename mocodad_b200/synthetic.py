@@ -77,3 +77,33 @@ def synth_noise(G: int, noise_steps: int, B: int, T: int, V: int = 17, seed: int
     r = _rng(seed, f"noise{G}x{noise_steps}x{B}x{T}x{V}")
     n = r.standard_normal(size=(G, max(noise_steps - 1, 1), B, 2, T, V)).astype(np.float32)
     return torch.from_numpy(n)
+
+
+def synth_scored_dataset(clips: Dict[Tuple[int, int], int], *, seg_len: int = 6, num_transform: int = 2,
+                         persons_per_clip: int = 3, seed: int = 5):
+    """A synthetic *test epoch* in the shape ``MoCoDAD.post_processing`` consumes (mocodad.py:337-430): for every
+    clip ``(scene, clip) -> n_frames`` a few persons, each present over 1-2 frame intervals, sliding windows of
+    ``seg_len`` frames with stride 1 over every interval, every window replicated for each affine transformation.
+    Returns (out [N] positive scores, trans [N], meta [N,4] = scene, clip, person, first frame, frames [N,seg_len]
+    1-based frame numbers, gt {(scene, clip): 0/1 per frame})."""
+    r = _rng(seed, f"scored{sorted(clips.items())}x{seg_len}x{num_transform}")
+    out, trans, meta, frames, gt = [], [], [], [], {}
+    for (scene, clip), n_frames in clips.items():
+        g = np.zeros(n_frames, dtype=np.int64)
+        for _ in range(max(1, n_frames // 200)):
+            a = int(r.integers(0, n_frames - 10))
+            g[a:a + int(r.integers(5, max(6, n_frames // 6)))] = 1
+        gt[(scene, clip)] = g
+        for person in range(1, persons_per_clip + 1):
+            cuts = np.sort(r.choice(np.arange(1, n_frames - 1), size=3, replace=False))
+            spans = [(1, int(cuts[0])), (int(cuts[1]), int(cuts[2]))] if person % 2 else [(int(cuts[0]), n_frames)]
+            for lo, hi in spans:  # inclusive 1-based frame range in which the person is tracked
+                for start in range(lo, hi - seg_len + 2):
+                    anomalous = g[start - 1:start - 1 + seg_len].mean()
+                    for tr in range(num_transform):
+                        out.append(float(r.gamma(2.0, 0.01) * (1.0 + 2.0 * anomalous)))
+                        trans.append(tr)
+                        meta.append([scene, clip, person, start])
+                        frames.append(np.arange(start, start + seg_len))
+    return (np.asarray(out, dtype=np.float32), np.asarray(trans, dtype=np.int64), np.asarray(meta, dtype=np.int64),
+            np.stack(frames).astype(np.int64), gt)

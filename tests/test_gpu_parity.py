@@ -305,3 +305,31 @@ def test_launch_counter_and_profile_slots():
     assert sum(v["launches"] for v in prof.values()) == launched
     assert prof["st_gcnnsd3.0"]["launches"] == 3 and prof["st_gcnnsd3.0"]["windows"] == 3 * 32
     assert all(v["ms"] > 0 for v in prof.values() if v["launches"])
+
+
+def test_auc_parity_through_post_processing():
+    """End of the path: per-window scores -> score assembly -> frame-level AUC (mocodad.py:337-430, restated in
+    mocodad_b200/postproc.py and pinned to the reference by tests/test_postproc.py).  north_star: AUC within +-0.1
+    (percentage points) of the reference path on identical inputs and noise."""
+    from mocodad_b200 import postproc, synthetic
+    clips = {(1, 1): 140, (1, 2): 120}
+    _, trans, meta, frames, gt = synthetic.synth_scored_dataset(clips, num_transform=2, persons_per_clip=2, seed=9)
+    n = len(trans)
+    N, G = 10, 3
+    eng, sd = _engine(6, N)
+    data = synth.synth_batch(n, 6, seed=31)[0]
+    # windows inside anomalous frames get jittered joints, so the score carries some signal
+    lab = np.array([gt[(int(m[0]), int(m[1]))][int(f[0]) - 1:int(f[-1])].mean() for m, f in zip(meta, frames)])
+    data = data + torch.from_numpy((lab[:, None, None, None] * np.random.default_rng(3).normal(0, 1.5, data.shape)).astype(np.float32))
+    noise = synth.synth_noise(G, N, n, 3, seed=32)
+    with torch.no_grad():
+        want, _ = ref_port.reverse_diffusion(sd, data, noise_steps=N, n_generated_samples=G, noise=noise)
+    got = eng.reverse_diffusion(data.to(DEV), G, noise=noise.to(DEV))["best"].cpu()
+    kw = dict(num_transform=2, pad_size=-1, frames_shift=2, filter_kernel_size=3)
+    auc_ref = postproc.dataset_auc(want.numpy(), trans, meta, frames, gt, **kw)
+    auc_got = postproc.dataset_auc(got.numpy(), trans, meta, frames, gt, **kw)
+    assert abs(auc_got - auc_ref) <= 1e-3, (auc_got, auc_ref)          # 0.1 percentage points
+    # in-kernel Philox noise: a different but equally distributed stream -> statistically the same detector
+    phil = eng.reverse_diffusion(data.to(DEV), G, seed=999)["best"].cpu()
+    auc_phil = postproc.dataset_auc(phil.numpy(), trans, meta, frames, gt, **kw)
+    assert abs(auc_phil - auc_ref) <= 0.03, (auc_phil, auc_ref)
