@@ -274,11 +274,31 @@ def run_b200(a):
     achieved = top_bytes_per_launch / top_sec_per_launch / 1e9
     per_call = [k for k in prof if k.startswith("st_gcnn") or k in ("down1", "down2", "up3", "up2", "ddpm_step")]
     unet_flops = sum(prof[k]["flops_per_window"] for k in per_call)  # one denoiser call + DDPM update, per window
+    # measured DRAM traffic of that kernel (ncu --set full, profiles/r01_ncu_traffic.json), scaled to this launch size
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tpath):
+        per_window = json.load(open(tpath))["dram_bytes_per_window"].get(top["kernel"])
+        if per_window is not None:
+            traffic = per_window * pv["windows"] / pv["launches"]
+    # tensor-pipe view of the same kernel: 3xTF32 executes 3 tf32 MMAs per fp32 product of the 1x1 convolution(s)
+    peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+    tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
+    conv = {"st_gcnnsd1.1": (32, 32, 17), "st_gcnnsd2.0": (32, 64, 12), "st_gcnnsd2.1": (64, 64, 12), "st_gcnnsd3.0": (64, 128, 10),
+            "st_gcnnsd3.1": (128, 64, 10), "st_gcnnsu4.0": (64, 64, 12), "st_gcnnsu4.1": (64, 32, 12), "st_gcnnsu3.0": (32, 32, 17)}
+    tensor = None
+    if top["kernel"] in conv:
+        ci, co, v = conv[top["kernel"]]
+        mma_flops = 3 * 2.0 * ci * co * T * v * (2 if ci != co else 1) * pv["windows"] / pv["launches"]
+        tensor = {"achieved_tflops": round(mma_flops / top_sec_per_launch / 1e12, 1), "peak_tflops": round(tf32_peak, 1),
+                  "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (kind::tf32 runs at half the bf16 rate)",
+                  "frac": round(mma_flops / top_sec_per_launch / 1e12 / tf32_peak, 4),
+                  "note": "tcgen05.mma kind::tf32, three MMAs per fp32 product (hi*hi + hi*lo + lo*hi)"}
     roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src, "tensor": tensor,
                 "us_per_launch": round(top_sec_per_launch * 1e6, 1),
                 "algorithmic_bytes_per_launch": top_bytes_per_launch,
-                "note": "the path is fp32-FMA-bound, not HBM-bound (SURVEY.md 8d): see 'fp32'",
+                "note": "the dominant kernel is bound by the fp32 FMA pipe + shared memory (position mixes), with its channel contraction on the tensor pipe; HBM is not the limiter (SURVEY.md 8d): see 'fp32' and 'tensor'",
                 "fp32": {"achieved_tflops": round(top_flops_per_launch / top_sec_per_launch / 1e12, 2),
                          "peak_tflops": round(fp32_peak, 2), "peak_source": "mcd_probe_fp32_detail: max of FFMA / FFMA2 register loops on this GPU",
                          "probe_ffma_tflops": round(ffma_peak, 2), "probe_ffma2_tflops": round(ffma2_peak, 2),
