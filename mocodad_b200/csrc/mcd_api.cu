@@ -232,7 +232,14 @@ int edge_block_op(int action, const mcd_model* m, int slot, const BlockWeights* 
   if (action == 0) return MCD_OK;
   if (io->n <= 0) return MCD_OK;
   const int64_t ntiles = (io->n + Cfg::NW - 1) / Cfg::NW;
-  const int64_t cap = int64_t(m->num_sms) * 2;
+  // latency-bound (three CTA-wide barriers per tile): fill every SM with as many CTAs as fit
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, edge_block_kernel<Cfg>, Cfg::THREADS, 0) != cudaSuccess || nb < 1) nb = 2;
+    per_sm = nb;
+  }
+  const int64_t cap = int64_t(m->num_sms) * per_sm;
   const int grid = int(ntiles < cap ? ntiles : cap);
   {
     LaunchScope ls(m, slot, io->n, s);

@@ -15,9 +15,9 @@
 //
 // Structure of one CTA (persistent, one per SM), 4 warpgroups (register budgets re-balanced with setmaxnreg),
 // every hand-off through shared-memory mbarriers:
-//   warp 13     loader: cp.async.bulk (TMA 1-D) copies of the next 16-channel activation chunk X -- one per
-//               (window, 4-channel plane), contiguous in the planar-4 source -- and of the chunk's pre-swizzled
-//               weight operands, completing on mbarriers;
+//   warp 13     activation loader: cp.async.bulk (TMA 1-D) copies of the next 16-channel chunk X -- one per
+//               (window, 4-channel plane), contiguous in the planar-4 source, issued lane-parallel;
+//   warp 14     weight loader: one bulk copy of the chunk's pre-swizzled weight operands; completing on mbarriers;
 //   warps 0-3   T-mix  Y1[q,v,c] = sum_t X[t,v,c] T[v,t,q]: a thread owns (joint v, a group of output frames) and
 //               keeps its slice of the learned T matrix in REGISTERS for the whole launch, so the only shared
 //               traffic is one 16-byte activation read per 8 packed FMAs (the v2 kernel was shared-memory bound);
@@ -40,7 +40,7 @@ constexpr int kTcMix = 128;        // threads per mix group (T-warps 0-3, A-warp
 constexpr int kTcEpiWarp0 = 8;     // epilogue warps 8-11 (TMEM lane quarters 0,1,2,3)
 constexpr int kTcMmaWarp = 12;     // the MMA-issuing warp
 constexpr int kTcEpilogue = 128;
-constexpr int kTcLoadWarp = 13;    // the loader warp (warps 14-15 only pad the last warpgroup)
+constexpr int kTcLoadWarp = 13;    // the activation loader warp; warp 14 loads weights (warp 15 only pads the last warpgroup)
 constexpr int kTcThreads = 16 * 32;
 // Register budgets per warpgroup (setmaxnreg): the T-mix threads keep 96 weights + two accumulator sets in registers.
 constexpr int kRegsT = 208, kRegsA = 168, kRegsE = 88, kRegsS = 48;
@@ -141,6 +141,13 @@ __device__ __forceinline__ float4 lds4_early(const float* p) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
   return v;
+}
+
+// predicated 16-byte shared store (a guaranteed @p STS, not a branch)
+__device__ __forceinline__ void sts4_pred(float* p, const float4 v, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p st.shared.v4.f32 [%0], {%1,%2,%3,%4};\n\t}\n" ::"r"(smem_u32(p)), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w), "r"(int(pred))
+               : "memory");
 }
 
 // float index of (row r, 4-channel group c4) in a [rows][16] fp32 operand array laid out K-major SWIZZLE_64B
@@ -339,57 +346,45 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
         const float* sXc = sX + b * ARR;
         float* sY = sY1 + s * Y1ARR;
         for (int wl = ws; wl < NW; wl += Cfg::WS_T) {
+          // One 4-channel group per pass: the fully unrolled body (T*QG*2 packed FMAs -- the weights live in registers, so
+          // the frame loop cannot be rolled) must stay small enough for the ~6 KB L0 instruction cache it shares with the
+          // A-mix warp of the same sub-partition (ncu: 28 % of the mix warps' stall samples were instruction fetches with
+          // two groups per pass).  Latency is covered by a software pipeline over blocks of TB frames instead.
 #pragma unroll 1
-          for (int cp = 0; cp < C4; cp += 2) {  // two 4-channel groups at once: two independent load streams
-            float2 a[2][2][QG];
+          for (int c4 = 0; c4 < C4; ++c4) {
+            float2 a[2][QG];
 #pragma unroll
-            for (int q = 0; q < QG; ++q) a[0][0][q] = a[0][1][q] = a[1][0][q] = a[1][1][q] = make_float2(0.f, 0.f);
-            // software pipeline over blocks of TB frames: the 2*TB loads of the next block are issued before the
-            // 16*TB packed FMAs of the current one (one sub-partition hosts a single T-mix warp: nothing else hides
-            // the ~50-cycle shared-memory latency)
-            constexpr int TB = T % 3 == 0 ? 3 : (T % 2 == 0 ? 2 : 1);
-            const float* xp0 = sXc + ((wl * 4 + cp) * P + v) * 4;  // planar X: [window][c4][position] 16-byte elements
-            const float* xp1 = xp0 + P * 4;
-            float4 xc[TB][2], xn[TB][2];
+            for (int q = 0; q < QG; ++q) a[0][q] = a[1][q] = make_float2(0.f, 0.f);
+            constexpr int TB = T % 6 == 0 ? 6 : (T % 3 == 0 ? 3 : (T % 2 == 0 ? 2 : 1));
+            const float* xp = sXc + ((wl * 4 + c4) * P + v) * 4;  // planar X: [window][c4][position] 16-byte elements
+            float4 xc[TB], xn[TB];
 #pragma unroll
-            for (int i = 0; i < TB; ++i) {
-              xn[i][0] = lds4_early(xp0 + i * V * 4);
-              xn[i][1] = lds4_early(xp1 + i * V * 4);
-            }
+            for (int i = 0; i < TB; ++i) xn[i] = lds4_early(xp + i * V * 4);
 #pragma unroll
             for (int tb = 0; tb < T; tb += TB) {
 #pragma unroll
-              for (int i = 0; i < TB; ++i) { xc[i][0] = xn[i][0]; xc[i][1] = xn[i][1]; }
+              for (int i = 0; i < TB; ++i) xc[i] = xn[i];
               if (tb + TB < T) {
 #pragma unroll
-                for (int i = 0; i < TB; ++i) {
-                  xn[i][0] = lds4_early(xp0 + (tb + TB + i) * V * 4);
-                  xn[i][1] = lds4_early(xp1 + (tb + TB + i) * V * 4);
-                }
+                for (int i = 0; i < TB; ++i) xn[i] = lds4_early(xp + (tb + TB + i) * V * 4);
               }
 #pragma unroll
               for (int i = 0; i < TB; ++i) {
                 const int t = tb + i;
-                const float2 x0l = make_float2(xc[i][0].x, xc[i][0].y), x0h = make_float2(xc[i][0].z, xc[i][0].w);
-                const float2 x1l = make_float2(xc[i][1].x, xc[i][1].y), x1h = make_float2(xc[i][1].z, xc[i][1].w);
+                const float2 xl = make_float2(xc[i].x, xc[i].y), xh = make_float2(xc[i].z, xc[i].w);
 #pragma unroll
                 for (int q = 0; q < QG; ++q) {
                   const float2 ww = make_float2(wT[t][q], wT[t][q]);
-                  a[0][0][q] = ffma2(x0l, ww, a[0][0][q]);
-                  a[0][1][q] = ffma2(x0h, ww, a[0][1][q]);
-                  a[1][0][q] = ffma2(x1l, ww, a[1][0][q]);
-                  a[1][1][q] = ffma2(x1h, ww, a[1][1][q]);
+                  a[0][q] = ffma2(xl, ww, a[0][q]);
+                  a[1][q] = ffma2(xh, ww, a[1][q]);
                 }
               }
             }
+            float* yp = sY + (((wl * 4 + c4) * QG) * TTP + rem) * 4;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              float* yp = sY + (((wl * 4 + cp + h) * QG) * TTP + rem) * 4;
-#pragma unroll
-              for (int q = 0; q < QG; ++q)
-                if (qg * QG + q < T)
-                  *reinterpret_cast<float4*>(yp + q * TTP * 4) = make_float4(a[h][0][q].x, a[h][0][q].y, a[h][1][q].x, a[h][1][q].y);
-            }
+            for (int q = 0; q < QG; ++q)
+              if (T % QG == 0 || qg * QG + q < T)
+                *reinterpret_cast<float4*>(yp + q * TTP * 4) = make_float4(a[0][q].x, a[0][q].y, a[1][q].x, a[1][q].y);
           }
         }
       }
@@ -430,59 +425,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
         for (int wl = ws; wl < NW; wl += Cfg::WS_A) {
           const int r0 = wl * P + t * V;
 #pragma unroll 1
-          for (int cp = 0; cp < C4; cp += 2) {  // two 4-channel groups at once: two independent load streams
-            float2 a[2][2][WGS];
+          for (int c4 = 0; c4 < C4; ++c4) {  // one 4-channel group per pass (small unrolled body, see the T-mix)
+            float2 a[2][WGS];
 #pragma unroll
-            for (int j = 0; j < WGS; ++j) a[0][0][j] = a[0][1][j] = a[1][0][j] = a[1][1][j] = make_float2(0.f, 0.f);
-            const float* yp0 = sY + (((wl * 4 + cp) * QG + t % QG) * TTP + t / QG) * 4;  // element (v, t) at + v * NQG
-            const float* yp1 = yp0 + QG * TTP * 4;
-            constexpr int VB = 3;  // joints per pipeline block (the last block may be partial)
-            float4 yc[VB][2], yn[VB][2];
+            for (int j = 0; j < WGS; ++j) a[0][j] = a[1][j] = make_float2(0.f, 0.f);
+            const float* yp = sY + (((wl * 4 + c4) * QG + t % QG) * TTP + t / QG) * 4;  // element (v, t) at + v * NQG
+            constexpr int VB = V >= 12 ? 6 : (V >= 6 ? 5 : V);  // joints per pipeline block (the last block may be partial)
+            float4 yc[VB], yn[VB];
 #pragma unroll
             for (int i = 0; i < VB; ++i)
-              if (i < V) {
-                yn[i][0] = lds4_early(yp0 + i * NQG * 4);
-                yn[i][1] = lds4_early(yp1 + i * NQG * 4);
-              }
+              if (i < V) yn[i] = lds4_early(yp + i * NQG * 4);
 #pragma unroll
             for (int vb = 0; vb < V; vb += VB) {
 #pragma unroll
-              for (int i = 0; i < VB; ++i) { yc[i][0] = yn[i][0]; yc[i][1] = yn[i][1]; }
+              for (int i = 0; i < VB; ++i) yc[i] = yn[i];
 #pragma unroll
               for (int i = 0; i < VB; ++i)
-                if (vb + VB + i < V) {
-                  yn[i][0] = lds4_early(yp0 + (vb + VB + i) * NQG * 4);
-                  yn[i][1] = lds4_early(yp1 + (vb + VB + i) * NQG * 4);
-                }
+                if (vb + VB + i < V) yn[i] = lds4_early(yp + (vb + VB + i) * NQG * 4);
 #pragma unroll
               for (int i = 0; i < VB; ++i) {
                 const int v = vb + i;
                 if (v < V) {
-                  const float2 y0l = make_float2(yc[i][0].x, yc[i][0].y), y0h = make_float2(yc[i][0].z, yc[i][0].w);
-                  const float2 y1l = make_float2(yc[i][1].x, yc[i][1].y), y1h = make_float2(yc[i][1].z, yc[i][1].w);
+                  const float2 yl = make_float2(yc[i].x, yc[i].y), yh = make_float2(yc[i].z, yc[i].w);
 #pragma unroll
                   for (int j = 0; j < WGS; ++j) {
                     const float2 ww = make_float2(wA[v][j], wA[v][j]);
-                    a[0][0][j] = ffma2(y0l, ww, a[0][0][j]);
-                    a[0][1][j] = ffma2(y0h, ww, a[0][1][j]);
-                    a[1][0][j] = ffma2(y1l, ww, a[1][0][j]);
-                    a[1][1][j] = ffma2(y1h, ww, a[1][1][j]);
+                    a[0][j] = ffma2(yl, ww, a[0][j]);
+                    a[1][j] = ffma2(yh, ww, a[1][j]);
                   }
                 }
               }
             }
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-              for (int j = 0; j < WGS; ++j) {
-                const int w = wg + j * NWG;
-                if (w < V) {
-                  const float4 o = make_float4(a[h][0][j].x, a[h][0][j].y, a[h][1][j].x, a[h][1][j].y);
-                  const int off = sw_off(r0 + w, cp + h);
-                  *reinterpret_cast<float4*>(sZ + off) = o;
-                  *reinterpret_cast<float4*>(sZlo + off) = tf32_lo4(o);
-                }
-              }
+            for (int j = 0; j < WGS; ++j) {  // predicated stores (no branches: every taken branch costs an instruction fetch)
+              const int w = wg + j * NWG;
+              const bool okw = (V % WGS == 0 && NWG * WGS == V) || w < V;
+              const float4 o = make_float4(a[0][j].x, a[0][j].y, a[1][j].x, a[1][j].y);
+              const int off = sw_off(r0 + (okw ? w : 0), c4);
+              sts4_pred(sZ + off, o, okw);
+              sts4_pred(sZlo + off, tf32_lo4(o), okw);
+            }
           }
         }
       }
@@ -555,31 +537,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       TRACE(2, it, 3);
     }
     } else if (warp == kTcLoadWarp) {
-    // =============================== loader warp ===============================
+    // =============================== activation loader warp ===============================
     for (int it = 0; it < npairs; ++it) {
       const int ti = it / NCHUNK, chunk = it - ti * NCHUNK;
       const int64_t tile = blockIdx.x + int64_t(ti) * gridDim.x;
-      const int b = it % NXB, s = it & 1;
+      const int b = it % NXB;
       TRACE(3, it, 0);
       if (it >= NXB) mbar_wait(BAR(BAR_X_EMPTY + b), uint32_t((it / NXB - 1) & 1));
       TRACE(3, it, 1);
-      if (lane == 0) {
-        // one bulk copy per (window, 4-channel plane): P x 16 contiguous bytes of the planar-4 source land as one
-        // plane of the planar X buffer; windows past the end of the tensor are skipped (their rows are never stored)
-        int64_t nvalid = io.n - tile * NW;
-        if (nvalid > NW) nvalid = NW;
-        constexpr uint32_t PLANE = P * 16;
-        mbar_expect_tx(BAR(BAR_X_FULL + b), uint32_t(nvalid) * 4u * PLANE);
-        const uint32_t dst0 = smem_u32(sX + b * ARR);
-        for (int wl = 0; wl < int(nvalid); ++wl)
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            bulk_g2s(dst0 + uint32_t(wl * 4 + j) * PLANE, io.in + act_off(tile * NW + wl, chunk * C4 + j, 0, CIN, P), PLANE,
-                     BAR(BAR_X_FULL + b));
+      // one bulk copy per (window, 4-channel plane): P x 16 contiguous bytes of the planar-4 source land as one
+      // plane of the planar X buffer; windows past the end of the tensor are skipped (their rows are never stored).
+      // The copies are issued by different lanes (a single lane needed ~1-2.6 k cycles for the 4*NW issues).
+      int64_t nvalid = io.n - tile * NW;
+      if (nvalid > NW) nvalid = NW;
+      constexpr uint32_t PLANE = P * 16;
+      if (lane == 0) mbar_expect_tx(BAR(BAR_X_FULL + b), uint32_t(nvalid) * 4u * PLANE);
+      __syncwarp();
+      const uint32_t dst0 = smem_u32(sX + b * ARR);
+      for (int k = lane; k < int(nvalid) * 4; k += 32) {
+        const int wl = k >> 2, j = k & 3;
+        bulk_g2s(dst0 + uint32_t(k) * PLANE, io.in + act_off(tile * NW + wl, chunk * C4 + j, 0, CIN, P), PLANE, BAR(BAR_X_FULL + b));
       }
       TRACE(3, it, 2);
+      __syncwarp();
+    }
+    } else if (warp == kTcLoadWarp + 1) {
+    // =============================== weight loader warp ===============================
+    // its own warp, so that waiting for a free weight buffer (MMAs of iteration it-2) never delays the activations
+    for (int it = 0; it < npairs; ++it) {
+      const int chunk = it % NCHUNK, s = it & 1;
       if (it >= 2) mbar_wait(BAR(BAR_MMA_DONE + s), uint32_t((it / 2 - 1) & 1));  // W[s] free again
-      TRACE(3, it, 3);
       if (lane == 0) {
         mbar_expect_tx(BAR(BAR_W_FULL + s), uint32_t(WCH * 4));
         bulk_g2s(smem_u32(sWc + s * WCH), wt.Bop + size_t(chunk) * WCH, uint32_t(WCH * 4), BAR(BAR_W_FULL + s));
