@@ -40,7 +40,8 @@ constexpr int kTcMix = 128;        // threads per mix group (T-warps 0-3, A-warp
 constexpr int kTcEpiWarp0 = 8;     // epilogue warps 8-11 (TMEM lane quarters 0,1,2,3)
 constexpr int kTcMmaWarp = 12;     // the MMA-issuing warp
 constexpr int kTcEpilogue = 128;
-constexpr int kTcLoadWarp = 13;    // the activation loader warp; warp 14 loads weights (warp 15 only pads the last warpgroup)
+constexpr int kTcLoadWarp = 13;    // the activation loader warp; warp 14 loads weights; warp 15 computes the lo part of X
+                                   // for blocks with a residual convolution
 constexpr int kTcThreads = 16 * 32;
 // Register budgets per warpgroup (setmaxnreg): the T-mix threads keep 96 weights + two accumulator sets in registers.
 constexpr int kRegsT = 208, kRegsA = 168, kRegsE = 88, kRegsS = 48;
@@ -61,6 +62,14 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
   constexpr uint32_t hi = (512u >> 4) | (1u << 14) | (4u << 29);
   const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);
+  return (uint64_t(hi) << 32) | lo;
+}
+// UMMA shared-memory matrix descriptor, K-major, no swizzle ("interleave"): 8-row x 16-byte core matrices stored as 128
+// contiguous bytes; SBO = distance between core matrices adjacent in M (128 bytes: rows are contiguous 16-byte
+// elements), LBO = distance between the two core matrices of a K=8 step (`lbo_bytes`: the next 4-channel plane).
+__device__ __forceinline__ uint64_t umma_desc_planar(uint32_t saddr, uint32_t lbo_bytes) {
+  constexpr uint32_t hi = (128u >> 4) | (1u << 14);
+  const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
   return (uint64_t(hi) << 32) | lo;
 }
 // instruction descriptor, kind::tf32: D fp32, A/B tf32 K-major, M=128
@@ -222,9 +231,11 @@ struct TcCfg {
   static constexpr int WCH = NPART * COUT * 16;  // one chunk of weight operands
   static constexpr int SM_X = 0;                 // NXB buffers
   static constexpr int SM_Y1 = SM_X + NXB * ARR;  // 2
-  static constexpr int SM_XHI = SM_Y1 + 2 * Y1ARR;              // 1: X in operand layout (residual convolution only)
-  static constexpr int SM_XLO = SM_XHI + (RESCONV ? ARR : 0);   // 1: its tf32 lo part
-  static constexpr int SM_Y2 = SM_XLO + (RESCONV ? ARR : 0);    // 2
+  // residual convolution: the planar X buffer itself is the "hi" operand (no-swizzle K-major descriptor); only its
+  // tf32 lo part is materialised, in the same planar layout, by the conversion warp (2 buffers)
+  static constexpr int NXLO = RESCONV ? 2 : 0;
+  static constexpr int SM_XLO = SM_Y1 + 2 * Y1ARR;
+  static constexpr int SM_Y2 = SM_XLO + NXLO * ARR;             // 2
   static constexpr int SM_Y2LO = SM_Y2 + 2 * ARR;             // 2
   static constexpr int SM_WC = SM_Y2LO + 2 * ARR;             // 2; also absorbs the last tile's over-read
   static constexpr int SM_BIAS = SM_WC + 2 * WCH;
@@ -246,7 +257,9 @@ enum TcBar {
   BAR_MMA_DONE = 14,              // [2] tcgen05.commit -> A-warps, loader (operand buffers free)
   BAR_ACC_FULL = 16,              // [2] tcgen05.commit -> epilogue
   BAR_ACC_EMPTY = 18,             // [2] epilogue -> MMA warp
-  BAR_COUNT = 20
+  BAR_XLO_FULL = 20,              // [2] conversion warp -> MMA warp (residual convolution)
+  BAR_RES_DONE = 22,              // [2] tcgen05.commit -> conversion warp (Xlo buffer free)
+  BAR_COUNT = 24
 };
 
 template <class Cfg>
@@ -262,7 +275,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
   float* smem = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   float* sX = smem + Cfg::SM_X;
   float* sY1 = smem + Cfg::SM_Y1;
-  float* sXhi = smem + Cfg::SM_XHI;
   float* sXlo = smem + Cfg::SM_XLO;
   float* sY2 = smem + Cfg::SM_Y2;
   float* sY2lo = smem + Cfg::SM_Y2LO;
@@ -301,7 +313,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
   } else if (tid == 0) {
     for (int i = 0; i < 3; ++i) {
       mbar_init(BAR(BAR_X_FULL + i), 1);  // one expect_tx arrival + the bulk copies' bytes
-      mbar_init(BAR(BAR_X_EMPTY + i), RESCONV ? 2 * kTcMix : kTcMix);
+      mbar_init(BAR(BAR_X_EMPTY + i), RESCONV ? kTcMix + 1 : kTcMix);  // T-warps (+ the commit of the residual MMAs)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(BAR(BAR_W_FULL + i), 1);
@@ -311,6 +323,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       mbar_init(BAR(BAR_MMA_DONE + i), 1);
       mbar_init(BAR(BAR_ACC_FULL + i), 1);
       mbar_init(BAR(BAR_ACC_EMPTY + i), kTcEpilogue);
+      mbar_init(BAR(BAR_XLO_FULL + i), 32);
+      mbar_init(BAR(BAR_RES_DONE + i), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -356,7 +370,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
 #pragma unroll
             for (int q = 0; q < QG; ++q) a[0][q] = a[1][q] = make_float2(0.f, 0.f);
             constexpr int TB = T % 6 == 0 ? 6 : (T % 3 == 0 ? 3 : (T % 2 == 0 ? 2 : 1));
-            const float* xp = sXc + ((wl * 4 + c4) * P + v) * 4;  // planar X: [window][c4][position] 16-byte elements
+            const float* xp = sXc + ((c4 * NW + wl) * P + v) * 4;  // planar X: [c4][window][position] 16-byte elements
             float4 xc[TB], xn[TB];
 #pragma unroll
             for (int i = 0; i < TB; ++i) xn[i] = lds4_early(xp + i * V * 4);
@@ -412,7 +426,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
         wA[v][j] = (active && wg + j * NWG < V) ? __ldg(wt.A + (t * V + v) * VP + wg + j * NWG) : 0.f;
 
     for (int it = 0; it < npairs; ++it) {
-      const int b = it % NXB, s = it & 1;
+      const int s = it & 1;
       if (warp == 4) TRACE(1, it, 0);
       mbar_wait(BAR(BAR_Y1_FULL + s), uint32_t((it / 2) & 1));
       if (warp == 4) TRACE(1, it, 1);
@@ -470,20 +484,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       }
       if (warp == 4) TRACE(1, it, 3);
       mbar_arrive(BAR(BAR_Y1_EMPTY + s));
-      if constexpr (RESCONV) {  // X and its tf32 lo part in operand layout for the residual convolution
-        mbar_wait(BAR(BAR_X_FULL + b), uint32_t((it / NXB) & 1));
-        if (it >= 1) mbar_wait(BAR(BAR_MMA_DONE + ((it - 1) & 1)), uint32_t(((it - 1) / 2) & 1));  // single Xhi / Xlo buffer
-        const float* sXc = sX + b * ARR;
-        for (int idx = atid; idx < ROWS * C4; idx += kTcMix) {
-          const int c4 = idx / ROWS, r = idx - c4 * ROWS;  // consecutive threads -> consecutive positions
-          const int wl = r / P, pp = r - wl * P;
-          const float4 x = *reinterpret_cast<const float4*>(sXc + ((wl * 4 + c4) * P + pp) * 4);
-          const int off = sw_off(r, c4);
-          *reinterpret_cast<float4*>(sXhi + off) = x;
-          *reinterpret_cast<float4*>(sXlo + off) = tf32_lo4(x);
-        }
-        mbar_arrive(BAR(BAR_X_EMPTY + b));
-      }
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor pipe
       if (warp == 4) TRACE(1, it, 4);
       mbar_arrive(BAR(BAR_OPS_FULL + s));
@@ -497,22 +497,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
     const uint64_t dY2_0 = umma_desc_sw64(smem_u32(sY2)), dY2_1 = umma_desc_sw64(smem_u32(sY2 + ARR));
     const uint64_t dY2lo_0 = umma_desc_sw64(smem_u32(sY2lo)), dY2lo_1 = umma_desc_sw64(smem_u32(sY2lo + ARR));
     const uint64_t dW_0 = umma_desc_sw64(smem_u32(sWc)), dW_1 = umma_desc_sw64(smem_u32(sWc + WCH));
-    const uint64_t dXlo = umma_desc_sw64(smem_u32(sXlo));
-    const uint64_t xHi = umma_desc_sw64(smem_u32(sXhi));
-    constexpr uint64_t PART = (COUT * 64) >> 4;  // one weight part, in descriptor address units (16 bytes)
+    // residual convolution: X (planar, no swizzle) and its lo part; descriptor of buffer k = base + k * ARR bytes
+    const uint64_t dX_0 = umma_desc_planar(smem_u32(sX), ROWS * 16), dXlo_0 = umma_desc_planar(smem_u32(sXlo), ROWS * 16);
+    constexpr uint64_t ARR16 = (uint64_t(ARR) * 4) >> 4;   // one operand array, in descriptor address units (16 bytes)
+    constexpr uint64_t PART = (COUT * 64) >> 4;            // one weight part, in descriptor address units
     for (int it = 0; it < npairs; ++it) {
       const int ti = it / NCHUNK, chunk = it - ti * NCHUNK;
-      const int set = ti & 1, s = it & 1;
-      TRACE(2, it, 0);
-      mbar_wait(BAR(BAR_OPS_FULL + s), uint32_t((it / 2) & 1));
-      TRACE(2, it, 1);
-      mbar_wait(BAR(BAR_W_FULL + s), uint32_t((it / 2) & 1));
-      TRACE(2, it, 2);
-      if (chunk == 0 && ti >= 2) mbar_wait(BAR(BAR_ACC_EMPTY + set), uint32_t((ti / 2 - 1) & 1));  // set drained by the epilogue
-      tc_fence_after();
-      const uint64_t aHi = s ? dY2_1 : dY2_0, aLo = s ? dY2lo_1 : dY2lo_0, bW = s ? dW_1 : dW_0;
+      const int set = ti & 1, s = it & 1, b = it % NXB;
+      const uint64_t bW = s ? dW_1 : dW_0;
       const uint32_t d0 = tmem + set * Cfg::ACC_COLS;
-      const uint32_t acc0 = chunk > 0 ? 1u : 0u;
+      TRACE(2, it, 0);
+      mbar_wait(BAR(BAR_W_FULL + s), uint32_t((it / 2) & 1));
+      if (chunk == 0 && ti >= 2) mbar_wait(BAR(BAR_ACC_EMPTY + set), uint32_t((ti / 2 - 1) & 1));  // set drained by the epilogue
+      if constexpr (RESCONV) {
+        // residual 1x1 convolution of this chunk, straight from the landed X buffer: issued as soon as the lo part
+        // exists, i.e. long before the mixes of the chunk finish, so the X ring slot is released early
+        mbar_wait(BAR(BAR_XLO_FULL + s), uint32_t((it / 2) & 1));
+        tc_fence_after();
+        const uint64_t xHi = dX_0 + uint64_t(b) * ARR16, xLo = dXlo_0 + uint64_t(s) * ARR16;
+        if (elect_one()) {
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            const uint32_t d = d0 + m * COUT;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {  // two K=8 steps per 16-channel chunk: c4 planes (2h, 2h+1)
+              const uint64_t ao = uint64_t((m * 128 * 16 + h * 2 * ROWS * 16) >> 4), bo = uint64_t((h * 32) >> 4);
+              umma_tf32(d, xLo + ao, bW + 2 * PART + bo, idesc, (chunk > 0 || h > 0) ? 1u : 0u);
+              umma_tf32(d, xHi + ao, bW + 3 * PART + bo, idesc, 1u);
+              umma_tf32(d, xHi + ao, bW + 2 * PART + bo, idesc, 1u);
+            }
+          }
+          umma_commit(BAR(BAR_RES_DONE + s));  // Xlo[s] free again
+          umma_commit(BAR(BAR_X_EMPTY + b));   // ... and the X ring slot (together with the T-warps' arrivals)
+        }
+        __syncwarp();
+      }
+      TRACE(2, it, 1);
+      mbar_wait(BAR(BAR_OPS_FULL + s), uint32_t((it / 2) & 1));
+      TRACE(2, it, 2);
+      tc_fence_after();
+      const uint64_t aHi = s ? dY2_1 : dY2_0, aLo = s ? dY2lo_1 : dY2lo_0;
+      const uint32_t acc0 = (RESCONV || chunk > 0) ? 1u : 0u;
       if (elect_one()) {
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
@@ -523,11 +548,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
             umma_tf32(d, aLo + ao, bW + bo, idesc, h == 0 ? acc0 : 1u);
             umma_tf32(d, aHi + ao, bW + PART + bo, idesc, 1u);
             umma_tf32(d, aHi + ao, bW + bo, idesc, 1u);
-            if constexpr (RESCONV) {
-              umma_tf32(d, dXlo + ao, bW + 2 * PART + bo, idesc, 1u);
-              umma_tf32(d, xHi + ao, bW + 3 * PART + bo, idesc, 1u);
-              umma_tf32(d, xHi + ao, bW + 2 * PART + bo, idesc, 1u);
-            }
           }
         }
         umma_commit(BAR(BAR_MMA_DONE + s));
@@ -546,7 +566,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       if (it >= NXB) mbar_wait(BAR(BAR_X_EMPTY + b), uint32_t((it / NXB - 1) & 1));
       TRACE(3, it, 1);
       // one bulk copy per (window, 4-channel plane): P x 16 contiguous bytes of the planar-4 source land as one
-      // plane of the planar X buffer; windows past the end of the tensor are skipped (their rows are never stored).
+      // plane of the planar X buffer [c4][window][position] (rows = (window, position) are contiguous inside a
+      // 4-channel plane, which makes the buffer a valid no-swizzle K-major UMMA operand as it stands); windows past
+      // the end of the tensor are skipped (their rows are never stored).
       // The copies are issued by different lanes (a single lane needed ~1-2.6 k cycles for the 4*NW issues).
       int64_t nvalid = io.n - tile * NW;
       if (nvalid > NW) nvalid = NW;
@@ -556,7 +578,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       const uint32_t dst0 = smem_u32(sX + b * ARR);
       for (int k = lane; k < int(nvalid) * 4; k += 32) {
         const int wl = k >> 2, j = k & 3;
-        bulk_g2s(dst0 + uint32_t(k) * PLANE, io.in + act_off(tile * NW + wl, chunk * C4 + j, 0, CIN, P), PLANE, BAR(BAR_X_FULL + b));
+        bulk_g2s(dst0 + uint32_t(j * NW + wl) * PLANE, io.in + act_off(tile * NW + wl, chunk * C4 + j, 0, CIN, P), PLANE, BAR(BAR_X_FULL + b));
       }
       TRACE(3, it, 2);
       __syncwarp();
@@ -572,6 +594,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
         bulk_g2s(smem_u32(sWc + s * WCH), wt.Bop + size_t(chunk) * WCH, uint32_t(WCH * 4), BAR(BAR_W_FULL + s));
       }
       __syncwarp();
+    }
+    } else if constexpr (RESCONV) {
+    // =============================== conversion warp (15) ===============================
+    // tf32 lo part of the landed X chunk, same planar layout (an element-wise pass), for the residual convolution
+    for (int it = 0; it < npairs; ++it) {
+      const int b = it % NXB, k = it & 1;
+      mbar_wait(BAR(BAR_X_FULL + b), uint32_t((it / NXB) & 1));
+      if (it >= 2) mbar_wait(BAR(BAR_RES_DONE + k), uint32_t((it / 2 - 1) & 1));  // Xlo[k] no longer read by the tensor pipe
+      const float4* src = reinterpret_cast<const float4*>(sX + b * ARR);
+      float4* dst = reinterpret_cast<float4*>(sXlo + k * ARR);
+      constexpr int NEL = ROWS * C4, U = 4;
+      int idx = lane;
+      for (; idx + (U - 1) * 32 < NEL; idx += U * 32) {
+        float4 x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) x[u] = src[idx + u * 32];
+#pragma unroll
+        for (int u = 0; u < U; ++u) dst[idx + u * 32] = tf32_lo4(x[u]);
+      }
+      for (; idx < NEL; idx += 32) dst[idx] = tf32_lo4(src[idx]);
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor pipe
+      mbar_arrive(BAR(BAR_XLO_FULL + k));
     }
     }
   } else {

@@ -23,7 +23,7 @@ r = r[r[:, 3] > 0]
 t0 = int(r[:, 3].min())
 roles = {0: "T", 1: "A", 2: "MMA", 3: "LOAD", 4: "EPI"}
 evn = {0: {0: "top", 1: "x_full", 2: "y1_empty", 3: "done"}, 1: {0: "top", 1: "y1_full", 2: "y2_free", 3: "mix done", 4: "ops ready"},
-       2: {0: "top", 1: "ops_full", 2: "w_full", 3: "issued"}, 3: {0: "top", 1: "x_empty", 2: "x issued", 3: "w free"},
+       2: {0: "top", 1: "ops_full", 2: "w_full", 3: "issued"}, 3: {0: "top", 1: "x_empty", 2: "x issued"},
        4: {0: "top", 1: "acc_full", 2: "done"}}
 rows = sorted(r.tolist(), key=lambda q: q[3])
 print(f"{len(rows)} records; showing pairs 4..9")
