@@ -190,6 +190,27 @@ constexpr int tc_pick_group(int outer, int inner, int nw) {  // tasks per window
   }
   return best;
 }
+// Task shape of a register-resident mix for one-window tiles (T=24): a thread owns (channel split cs of CS, outer index,
+// group of g inner outputs), keeps len*g weights in registers (<= reg_max) and makes C4/CS passes over the 4-channel
+// groups of the chunk.  Cost model (measured behaviour of the v2 kernel: both the FMA pipe of the busiest
+// sub-partition and the CTA-wide shared-memory pipe matter; every warp-wide LDS.128 costs 4 wavefronts):
+//   fma  = passes * len * g * 2 packed FMAs * 2 cycles        smem = active warps * passes * len loads * 4 wavefronts
+struct TcShape { int g, cs; };
+constexpr TcShape tc_pick_shape(int outer, int inner, int len, int reg_max, int g_max, int c4) {
+  TcShape best{2, 1};
+  int best_cost = 1 << 30;
+  for (int g = 2; g <= g_max; ++g) {
+    if (len * g > reg_max) continue;
+    for (int cs = 1; cs <= c4; cs *= 2) {
+      const int tasks = cs * outer * tc_ceil(inner, g);
+      if (tasks > kTcMix) continue;
+      const int passes = c4 / cs, warps = tc_ceil(tasks, 32);
+      const int cost = passes * len * g * 2 * 2 + warps * passes * len * 4;
+      if (cost < best_cost) { best_cost = cost; best = TcShape{g, cs}; }
+    }
+  }
+  return best;
+}
 
 template <int T_, int V_, int CIN_, int COUT_, int NW_>
 struct TcCfg {
@@ -207,13 +228,21 @@ struct TcCfg {
   static constexpr int TP4 = (T + 3) / 4 * 4;
   static constexpr int TMS = T * TP4 + 4;
   // T-mix: thread = (window slot, joint v, group of QG output frames);  A-mix: thread = (window slot, frame t, WGS joints)
-  static constexpr int QG = T <= 4 ? T : tc_pick_group(V, T, NW);
+  //        (one-window tiles additionally split the chunk's four 4-channel groups over CS thread sets, tc_pick_shape)
+  static constexpr bool SHAPED = NW == 1 && T > 4;
+  static constexpr TcShape SH_T = tc_pick_shape(V, T, T, 100, 8, C4), SH_A = tc_pick_shape(T, V, V, 76, 5, C4);
+  // (A-mix groups of 6 joints at V=12 measured slower: two joint groups per frame make the operand stores conflict)
+  static constexpr int QG = T <= 4 ? T : (SHAPED ? SH_T.g : tc_pick_group(V, T, NW));
+  static constexpr int CS_T = SHAPED ? SH_T.cs : 1;
   static constexpr int NQG = tc_ceil(T, QG);
-  static constexpr int TT = V * NQG;                                   // T-mix tasks per window
+  static constexpr int TTR = V * NQG;                                  // (joint, frame group) pairs
+  static constexpr int TT = CS_T * TTR;                                // T-mix tasks per window
   static constexpr int WS_T = (kTcMix / TT) < NW ? (kTcMix / TT) : NW; // window slots
-  static constexpr int WGS = tc_pick_group(T, V, NW);
+  static constexpr int WGS = SHAPED ? SH_A.g : tc_pick_group(T, V, NW);
+  static constexpr int CS_A = SHAPED ? SH_A.cs : 1;
   static constexpr int NWG = tc_ceil(V, WGS);
-  static constexpr int TA = T * NWG;
+  static constexpr int TAR = T * NWG;                                  // (frame, joint group) pairs
+  static constexpr int TA = CS_A * TAR;
   static constexpr int WS_A = (kTcMix / TA) < NW ? (kTcMix / TA) : NW;
   static_assert(TT <= kTcMix && TA <= kTcMix && WS_T >= 1 && WS_A >= 1, "mix task mapping");
   static constexpr int ACC_COLS = MT * COUT;  // one accumulator set; TMEM holds two (tile parity)
@@ -226,7 +255,7 @@ struct TcCfg {
   // Y1 is not an MMA operand, so its layout is chosen for the two mixes: 16-byte (4-channel) elements indexed
   // [window][c4][q within the frame group][T-mix thread (v, qg)] with the thread pitch TTP = 2 (mod 8): the T-mix
   // threads of a warp store consecutive elements, the A-mix threads of a warp (consecutive frames) hit distinct banks
-  static constexpr int TTP = T >= 8 ? (TT + 5) / 8 * 8 + 2 : (TT | 1);
+  static constexpr int TTP = T >= 8 ? (TTR + 5) / 8 * 8 + 2 : (TTR | 1);
   static constexpr int Y1ARR = ((NW * 4 * QG * TTP * 4) + 127) / 128 * 128;
   static constexpr int WCH = NPART * COUT * 16;  // one chunk of weight operands
   static constexpr int SM_X = 0;                 // NXB buffers
@@ -339,7 +368,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
     // =============================== T-mix warps ===============================
     reg_inc<kRegsT>();
     // Y1[n,(q,v),c] = sum_t X[n,(t,v),c] * Tm[v][t][q]        stsgcn.py:154
-    const int ws = tid / Cfg::TT, rem = tid - ws * Cfg::TT;
+    const int ws = tid / Cfg::TT, rem_all = tid - ws * Cfg::TT;
+    const int cs = rem_all / Cfg::TTR, rem = rem_all - cs * Cfg::TTR;  // channel split, (joint, frame group)
     const int v = rem / NQG, qg = rem - v * NQG;
     const bool active = ws < Cfg::WS_T;
     float wT[T][QG];  // this thread's slice of the learned time-mix matrix, resident for the whole launch
@@ -365,7 +395,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
           // A-mix warp of the same sub-partition (ncu: 28 % of the mix warps' stall samples were instruction fetches with
           // two groups per pass).  Latency is covered by a software pipeline over blocks of TB frames instead.
 #pragma unroll 1
-          for (int c4 = 0; c4 < C4; ++c4) {
+          for (int c4 = cs; c4 < C4; c4 += Cfg::CS_T) {
             float2 a[2][QG];
 #pragma unroll
             for (int q = 0; q < QG; ++q) a[0][q] = a[1][q] = make_float2(0.f, 0.f);
@@ -411,7 +441,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
     reg_inc<kRegsA>();
     // Y2[n,(t,w),c] = sum_v Y1[n,(t,v),c] * A[t][v][w]       stsgcn.py:155   (+ tf32 lo parts for the tensor pipe)
     const int atid = tid - kTcMix;
-    const int ws = atid / Cfg::TA, rem = atid - ws * Cfg::TA;
+    const int ws = atid / Cfg::TA, rem_all = atid - ws * Cfg::TA;
+    const int cs = rem_all / Cfg::TAR, rem = rem_all - cs * Cfg::TAR;  // channel split, (frame, joint group)
     // thread wg of a frame owns output joints wg, wg+NWG, ...; frames are dealt to consecutive thread groups with a
     // stride FS coprime to T chosen so that the 8 lanes of a quarter warp store to 8 different bank groups
     constexpr int FS = (V % 8 == 1 && T % 5 != 0) ? 5 : 1;
@@ -439,12 +470,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
         for (int wl = ws; wl < NW; wl += Cfg::WS_A) {
           const int r0 = wl * P + t * V;
 #pragma unroll 1
-          for (int c4 = 0; c4 < C4; ++c4) {  // one 4-channel group per pass (small unrolled body, see the T-mix)
+          for (int c4 = cs; c4 < C4; c4 += Cfg::CS_A) {  // one 4-channel group per pass (small unrolled body, see the T-mix)
             float2 a[2][WGS];
 #pragma unroll
             for (int j = 0; j < WGS; ++j) a[0][j] = a[1][j] = make_float2(0.f, 0.f);
             const float* yp = sY + (((wl * 4 + c4) * QG + t % QG) * TTP + t / QG) * 4;  // element (v, t) at + v * NQG
-            constexpr int VB = V >= 12 ? 6 : (V >= 6 ? 5 : V);  // joints per pipeline block (the last block may be partial)
+            constexpr int VB = V * WGS > 60 ? 4 : (V >= 12 ? 6 : (V >= 6 ? 5 : V));  // joints per pipeline block (the last may be partial)
             float4 yc[VB], yn[VB];
 #pragma unroll
             for (int i = 0; i < VB; ++i)
