@@ -45,6 +45,19 @@ def is_current() -> bool:
         return False
 
 
+TRACE_LIB_PATH = os.path.join(PKG, "libmocodad_b200_trace.so")
+
+
+def build_trace_variant() -> str:
+    """Debug build with the device-timeline instrumentation of the tensor-core block kernel compiled in
+    (``-DMCD_TC_TRACE=1``); used by tools/trace_block.py through ``MOCODAD_B200_LIB``.  Never loaded by default."""
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-DMCD_TC_TRACE=1", "-o", TRACE_LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return TRACE_LIB_PATH
+
+
 def build_extension(force: bool = False, verbose: bool = False) -> str:
     """Compile the library if sources changed (or ``force``).  Returns the .so path."""
     if not force and is_current():
@@ -63,4 +76,7 @@ def build_extension(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     import sys
-    print(build_extension(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--trace" in sys.argv:
+        print(build_trace_variant())
+    else:
+        print(build_extension(force="--force" in sys.argv, verbose="-v" in sys.argv))

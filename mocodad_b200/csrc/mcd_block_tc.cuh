@@ -34,6 +34,10 @@
 #pragma once
 #include "mcd_kernels.cuh"
 
+#ifndef MCD_TC_TRACE
+#define MCD_TC_TRACE 0
+#endif
+
 namespace mcd {
 
 constexpr int kTcMix = 128;        // threads per mix group (T-warps 0-3, A-warps 4-7)
@@ -223,7 +227,6 @@ struct TcCfg {
   static constexpr int C4 = KC / 4;
   static constexpr bool RESCONV = CIN != COUT;
   static constexpr int NPART = RESCONV ? 4 : 2;  // weight operand parts per chunk: W hi, W lo [, Wr hi, Wr lo]
-  static constexpr int NXB = 2;                  // X ring depth (X lands planar: [window][c4][position] 16-byte elements)
   static constexpr int VP = (V + 3) / 4 * 4;
   static constexpr int TP4 = (T + 3) / 4 * 4;
   static constexpr int TMS = T * TP4 + 4;
@@ -258,11 +261,15 @@ struct TcCfg {
   static constexpr int TTP = T >= 8 ? (TTR + 5) / 8 * 8 + 2 : (TTR | 1);
   static constexpr int Y1ARR = ((NW * 4 * QG * TTP * 4) + 127) / 128 * 128;
   static constexpr int WCH = NPART * COUT * 16;  // one chunk of weight operands
-  static constexpr int SM_X = 0;                 // NXB buffers
-  static constexpr int SM_Y1 = SM_X + NXB * ARR;  // 2
   // residual convolution: the planar X buffer itself is the "hi" operand (no-swizzle K-major descriptor); only its
   // tf32 lo part is materialised, in the same planar layout, by the conversion warp (2 buffers)
   static constexpr int NXLO = RESCONV ? 2 : 0;
+  // X ring depth (X lands planar: [c4][window][position] 16-byte elements): 3 where shared memory allows -- the refill of
+  // a slot (release -> bulk copy issue -> ~1.5 k cycles of latency) then hides behind two mix iterations instead of one
+  static constexpr int SM_REST = 2 * Y1ARR + NXLO * ARR + 4 * ARR + 2 * WCH + COUT + NW * COUT + NW * kMaxE;
+  static constexpr int NXB = (size_t(SM_REST + 3 * ARR) * sizeof(float) + 1024 <= 227 * 1024) ? 3 : 2;
+  static constexpr int SM_X = 0;                 // NXB buffers
+  static constexpr int SM_Y1 = SM_X + NXB * ARR;  // 2
   static constexpr int SM_XLO = SM_Y1 + 2 * Y1ARR;
   static constexpr int SM_Y2 = SM_XLO + NXLO * ARR;             // 2
   static constexpr int SM_Y2LO = SM_Y2 + 2 * ARR;             // 2
@@ -321,7 +328,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
   const int npairs = my_tiles * NCHUNK;
   const uint32_t bar0 = smem_u32(&bars[0]);
   auto BAR = [&](int slot) { return bar0 + uint32_t(slot) * 8u; };
-  // debug timeline (mcd_debug_trace): lane 0 of each role's first warp in CTA 0 appends (role, pair, event, clock)
+  // debug timeline (mcd_debug_trace_next): lane 0 of each role's first warp in CTA 0 appends (role, pair, event, clock).
+  // Compiled in only with -DMCD_TC_TRACE=1 (tools/trace_block.py builds that variant): the inline trace code costs
+  // instruction fetches on every loop iteration of every role.
+#if MCD_TC_TRACE
   __shared__ int trace_n;
   if (tid == 0) trace_n = 0;
   auto TRACE = [&](int role, int it, int ev) {
@@ -332,6 +342,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       }
     }
   };
+#else
+  auto TRACE = [](int, int, int) {};
+#endif
 
   // ---- once per CTA ----
   if (warp == kTcMmaWarp) {

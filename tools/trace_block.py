@@ -1,7 +1,10 @@
 """Device-side timeline of one tensor-core block launch (debug aid): prints per-role event times for CTA 0.
+Needs the instrumented build: `python -m mocodad_b200._build --trace` (here, before gpurun; the .so travels).
 usage (on the GPU box): python tools/trace_block.py [slot=2] [n_windows=2368]"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ["MOCODAD_B200_LIB"] = os.path.join(ROOT, "mocodad_b200", "libmocodad_b200_trace.so")
 import torch
 from mocodad_b200 import ScoringEngine, synthetic as synth
 from mocodad_b200._lib import check
