@@ -253,7 +253,7 @@ int unet_block_op(int action, int idx, const mcd_model* m, const BlockWeights* w
   const int slot = SLOT_UNET0 + idx;
   switch (idx) {
     case 0: return edge_block_op<T, true>(action, m, slot, w, io, s);
-    case 1: return block_op<T, 17, 16, 32, true, IN_CL, OUT_CL>(action, m, slot, w, io, s);
+    case 1: return dense_block_op<T, 17, 16, 32>(action, m, slot, w, io, s);
     case 2: return dense_block_op<T, 17, 32, 32>(action, m, slot, w, io, s);
     case 3: return dense_block_op<T, 12, 32, 64>(action, m, slot, w, io, s);
     case 4: return dense_block_op<T, 12, 64, 64>(action, m, slot, w, io, s);

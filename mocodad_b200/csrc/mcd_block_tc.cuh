@@ -263,17 +263,21 @@ struct TcCfg {
   static constexpr int WCH = NPART * COUT * 16;  // one chunk of weight operands
   // residual convolution: the planar X buffer itself is the "hi" operand (no-swizzle K-major descriptor); only its
   // tf32 lo part is materialised, in the same planar layout, by the conversion warp (2 buffers)
-  static constexpr int NXLO = RESCONV ? 2 : 0;
-  // X ring depth (X lands planar: [c4][window][position] 16-byte elements): 3 where shared memory allows -- the refill of
-  // a slot (release -> bulk copy issue -> ~1.5 k cycles of latency) then hides behind two mix iterations instead of one
-  static constexpr int SM_REST = 2 * Y1ARR + NXLO * ARR + 4 * ARR + 2 * WCH + COUT + NW * COUT + NW * kMaxE;
-  static constexpr int NXB = (size_t(SM_REST + 3 * ARR) * sizeof(float) + 1024 <= 227 * 1024) ? 3 : 2;
+  // Buffer counts by what fits into 227 KB: the X ring (planar [c4][window][position] 16-byte elements) is 3 deep where
+  // possible -- the refill of a slot (release -> bulk copy issue -> ~1.5 k cycles of latency) then hides behind two mix
+  // iterations instead of one; the widest tiles (V=17 with a residual convolution) fall back to single Xlo / Y2 buffers.
+  static constexpr int SM_MISC = 2 * Y1ARR + 2 * WCH + COUT + NW * COUT + NW * kMaxE;
+  static constexpr bool tc_fits(int arrays) { return size_t(SM_MISC + arrays * ARR) * sizeof(float) + 1024 <= 227 * 1024; }
+  static constexpr int NXLO = !RESCONV ? 0 : (tc_fits(2 + 2 + 4) ? 2 : 1);
+  static constexpr int NY2 = tc_fits(2 + NXLO + 4) ? 2 : 1;
+  static constexpr int NXB = tc_fits(3 + NXLO + 2 * NY2) ? 3 : 2;
+  static_assert(tc_fits(NXB + NXLO + 2 * NY2), "tensor-core block tile exceeds shared memory");
   static constexpr int SM_X = 0;                 // NXB buffers
   static constexpr int SM_Y1 = SM_X + NXB * ARR;  // 2
   static constexpr int SM_XLO = SM_Y1 + 2 * Y1ARR;
-  static constexpr int SM_Y2 = SM_XLO + NXLO * ARR;             // 2
-  static constexpr int SM_Y2LO = SM_Y2 + 2 * ARR;             // 2
-  static constexpr int SM_WC = SM_Y2LO + 2 * ARR;             // 2; also absorbs the last tile's over-read
+  static constexpr int SM_Y2 = SM_XLO + NXLO * ARR;           // NY2
+  static constexpr int SM_Y2LO = SM_Y2 + NY2 * ARR;           // NY2
+  static constexpr int SM_WC = SM_Y2LO + NY2 * ARR;           // 2; also absorbs the last tile's over-read
   static constexpr int SM_BIAS = SM_WC + 2 * WCH;
   static constexpr int SM_EMB = SM_BIAS + COUT;
   static constexpr int SM_S = SM_EMB + NW * COUT;
@@ -474,12 +478,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       if (warp == 4) TRACE(1, it, 0);
       mbar_wait(BAR(BAR_Y1_FULL + s), uint32_t((it / 2) & 1));
       if (warp == 4) TRACE(1, it, 1);
-      if (it >= 2) mbar_wait(BAR(BAR_MMA_DONE + s), uint32_t((it / 2 - 1) & 1));  // Y2[s], Y2lo[s] free again
+      constexpr int NY2 = Cfg::NY2;  // Y2 / Y2lo buffer it % NY2 was last read by the MMAs of iteration it - NY2
+      if (it >= NY2) mbar_wait(BAR(BAR_MMA_DONE + ((it - NY2) & 1)), uint32_t(((it - NY2) / 2) & 1));
       if (warp == 4) TRACE(1, it, 2);
       if (active) {
         const float* sY = sY1 + s * Y1ARR;
-        float* sZ = sY2 + s * ARR;
-        float* sZlo = sY2lo + s * ARR;
+        float* sZ = sY2 + (it % NY2) * ARR;
+        float* sZlo = sY2lo + (it % NY2) * ARR;
         for (int wl = ws; wl < NW; wl += Cfg::WS_A) {
           const int r0 = wl * P + t * V;
 #pragma unroll 1
@@ -538,8 +543,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
     // =============================== MMA-issuing warp ===============================
     const uint32_t idesc = umma_idesc_tf32(COUT);
     // operand descriptors of every buffer, computed once (warp-uniform): inside the loop a descriptor is base + constant
-    const uint64_t dY2_0 = umma_desc_sw64(smem_u32(sY2)), dY2_1 = umma_desc_sw64(smem_u32(sY2 + ARR));
-    const uint64_t dY2lo_0 = umma_desc_sw64(smem_u32(sY2lo)), dY2lo_1 = umma_desc_sw64(smem_u32(sY2lo + ARR));
+    const uint64_t dY2_0 = umma_desc_sw64(smem_u32(sY2)), dY2lo_0 = umma_desc_sw64(smem_u32(sY2lo));
     const uint64_t dW_0 = umma_desc_sw64(smem_u32(sWc)), dW_1 = umma_desc_sw64(smem_u32(sWc + WCH));
     // residual convolution: X (planar, no swizzle) and its lo part; descriptor of buffer k = base + k * ARR bytes
     const uint64_t dX_0 = umma_desc_planar(smem_u32(sX), ROWS * 16), dXlo_0 = umma_desc_planar(smem_u32(sXlo), ROWS * 16);
@@ -558,7 +562,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
         // exists, i.e. long before the mixes of the chunk finish, so the X ring slot is released early
         mbar_wait(BAR(BAR_XLO_FULL + s), uint32_t((it / 2) & 1));
         tc_fence_after();
-        const uint64_t xHi = dX_0 + uint64_t(b) * ARR16, xLo = dXlo_0 + uint64_t(s) * ARR16;
+        const uint64_t xHi = dX_0 + uint64_t(b) * ARR16, xLo = dXlo_0 + uint64_t(it % Cfg::NXLO) * ARR16;
         if (elect_one()) {
 #pragma unroll
           for (int m = 0; m < MT; ++m) {
@@ -580,7 +584,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       mbar_wait(BAR(BAR_OPS_FULL + s), uint32_t((it / 2) & 1));
       TRACE(2, it, 2);
       tc_fence_after();
-      const uint64_t aHi = s ? dY2_1 : dY2_0, aLo = s ? dY2lo_1 : dY2lo_0;
+      const uint64_t aHi = dY2_0 + uint64_t(it % Cfg::NY2) * ARR16, aLo = dY2lo_0 + uint64_t(it % Cfg::NY2) * ARR16;
       const uint32_t acc0 = (RESCONV || chunk > 0) ? 1u : 0u;
       if (elect_one()) {
 #pragma unroll
@@ -643,11 +647,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
     // =============================== conversion warp (15) ===============================
     // tf32 lo part of the landed X chunk, same planar layout (an element-wise pass), for the residual convolution
     for (int it = 0; it < npairs; ++it) {
-      const int b = it % NXB, k = it & 1;
+      constexpr int NXLO = Cfg::NXLO > 0 ? Cfg::NXLO : 1;
+      const int b = it % NXB;
       mbar_wait(BAR(BAR_X_FULL + b), uint32_t((it / NXB) & 1));
-      if (it >= 2) mbar_wait(BAR(BAR_RES_DONE + k), uint32_t((it / 2 - 1) & 1));  // Xlo[k] no longer read by the tensor pipe
+      // Xlo buffer it % NXLO was last read by the residual MMAs of iteration it - NXLO
+      if (it >= NXLO) mbar_wait(BAR(BAR_RES_DONE + ((it - NXLO) & 1)), uint32_t(((it - NXLO) / 2) & 1));
       const float4* src = reinterpret_cast<const float4*>(sX + b * ARR);
-      float4* dst = reinterpret_cast<float4*>(sXlo + k * ARR);
+      float4* dst = reinterpret_cast<float4*>(sXlo + (it % NXLO) * ARR);
       constexpr int NEL = ROWS * C4, U = 4;
       int idx = lane;
       for (; idx + (U - 1) * 32 < NEL; idx += U * 32) {
@@ -659,7 +665,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       }
       for (; idx < NEL; idx += 32) dst[idx] = tf32_lo4(src[idx]);
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor pipe
-      mbar_arrive(BAR(BAR_XLO_FULL + k));
+      mbar_arrive(BAR(BAR_XLO_FULL + (it & 1)));
     }
     }
   } else {
