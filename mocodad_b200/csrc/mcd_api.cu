@@ -92,6 +92,7 @@ struct PackedResample {
   int vin = 0, vout = 0;
   const float* W = nullptr;
   const float* b = nullptr;
+  std::vector<float> hW, hb;  // host copies: the kernel takes the folded weights as a parameter (constant bank)
 };
 
 struct ProfEvent { cudaEvent_t a, b; int slot; int64_t windows; };
@@ -319,19 +320,42 @@ bool tc_supported(int Tc) {
   return false;
 }
 
+template <int VIN, int VOUT>
+void resample_op(int action, const PackedResample* r, const float* in, const float* skip, float* out, int64_t frames, int grid,
+                 cudaStream_t s) {
+  using Cfg = ResampleCfg<VIN, VOUT>;
+  if (action == 0) {
+    cudaFuncSetAttribute(joint_resample_kernel<VIN, VOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES));
+    return;
+  }
+  ResampleParams<VIN, VOUT> prm;
+  for (int w = 0; w < VOUT; ++w) {
+    for (int v = 0; v < VIN; ++v) prm.w[w][v] = r->hW[size_t(w) * VIN + v];
+    prm.b[w] = r->hb[w];
+  }
+  joint_resample_kernel<VIN, VOUT><<<grid, kRsFrames, Cfg::SMEM_BYTES, s>>>(in, skip, out, prm, frames);
+}
+
+// action 0: set the shared-memory attribute of every instantiation (mcd_model_finalize); 1: launch
+int resample_dispatch(int action, const mcd_model* m, int idx, const float* in, const float* skip, float* out, int64_t frames,
+                      int grid, cudaStream_t s) {
+  const PackedResample& r = m->rs[idx];
+  if (r.vin == 17 && r.vout == 12) resample_op<17, 12>(action, &r, in, skip, out, frames, grid, s);
+  else if (r.vin == 12 && r.vout == 10) resample_op<12, 10>(action, &r, in, skip, out, frames, grid, s);
+  else if (r.vin == 10 && r.vout == 12) resample_op<10, 12>(action, &r, in, skip, out, frames, grid, s);
+  else if (r.vin == 12 && r.vout == 17) resample_op<12, 17>(action, &r, in, skip, out, frames, grid, s);
+  else return fail(MCD_ERR_UNSUPPORTED, "joint resample %d->%d", r.vin, r.vout);
+  return MCD_OK;
+}
+
 int launch_resample(const mcd_model* m, int idx, const float* in, const float* skip, float* out, int64_t n, int C,
                     cudaStream_t s) {
-  const PackedResample& r = m->rs[idx];
-  const int64_t frames = n * m->T;
-  const int grid = grid_for(frames * (C / 4), kThreads, m->num_sms, 8);
-  const int T = m->T;
+  const int64_t frames = n * m->T * (C / 4);  // (window, 4-channel plane, frame): contiguous in planar-4 tensors
+  if (frames <= 0) return MCD_OK;
+  const int grid = grid_for(frames, kRsFrames, m->num_sms, 6);
   {
     LaunchScope ls(m, SLOT_RS0 + idx, n, s);
-    if (r.vin == 17 && r.vout == 12) joint_resample_kernel<17, 12><<<grid, kThreads, 0, s>>>(in, skip, out, r.W, r.b, n, T, C);
-    else if (r.vin == 12 && r.vout == 10) joint_resample_kernel<12, 10><<<grid, kThreads, 0, s>>>(in, skip, out, r.W, r.b, n, T, C);
-    else if (r.vin == 10 && r.vout == 12) joint_resample_kernel<10, 12><<<grid, kThreads, 0, s>>>(in, skip, out, r.W, r.b, n, T, C);
-    else if (r.vin == 12 && r.vout == 17) joint_resample_kernel<12, 17><<<grid, kThreads, 0, s>>>(in, skip, out, r.W, r.b, n, T, C);
-    else return fail(MCD_ERR_UNSUPPORTED, "joint resample %d->%d", r.vin, r.vout);
+    MCD_TRY(resample_dispatch(1, m, idx, in, skip, out, frames, grid, s));
   }
   return check_launch(kResample[idx].name);
 }
@@ -654,6 +678,9 @@ int check_ready(const mcd_model* m) {
 }
 
 int64_t tile_unit(const mcd_model* m) { return int64_t(m->num_sms) * nw_for(m->T, 17); }
+// default pass size of the virtual batch, in waves of CTA tiles: long enough that the pipeline fill / drain and the
+// launch prologue of the persistent block kernels are ~1 % of a launch (6.9 GB of workspace at T=24)
+constexpr int kDefaultWaves = 128;
 
 // fp32 FMA probe: 8 independent chains per thread, 4096 FMAs each
 __global__ void __launch_bounds__(256) fma_probe_kernel(float* out, int iters) {
@@ -835,6 +862,8 @@ int mcd_model_finalize(mcd_model* m) {
     }
     m->rs[i].vin = vin;
     m->rs[i].vout = vout;
+    m->rs[i].hW.assign(ar.h.begin() + rsW[i], ar.h.begin() + rsW[i] + size_t(vout) * vin);
+    m->rs[i].hb.assign(ar.h.begin() + rsb[i], ar.h.begin() + rsb[i] + vout);
   }
   size_t btlW = 0, btlb = 0;
   if (m->Tc > 0) {
@@ -881,6 +910,7 @@ int mcd_model_finalize(mcd_model* m) {
   }
   m->d_pos = m->d_arena + pos_off;
   for (int i = 0; i < kNumUnetBlocks; ++i) MCD_TRY(unet_block_dispatch(0, m->T, i, m, nullptr, nullptr, nullptr));
+  for (int i = 0; i < kNumResample; ++i) MCD_TRY(resample_dispatch(0, m, i, nullptr, nullptr, nullptr, 0, 0, nullptr));
   if (m->Tc > 0)
     for (int i = 0; i < kNumEncBlocks; ++i) MCD_TRY(enc_block_dispatch(0, m->Tc, i, m, nullptr, nullptr, nullptr));
   m->finalized = true;
@@ -1007,7 +1037,12 @@ int mcd_reverse_diffusion(const mcd_model* m, const float* d_data, int64_t B, in
   if (n_tile < 1) n_tile = 1;
   if (n_tile > nv) n_tile = nv;
   const int64_t unit = tile_unit(m);
-  if (n_tile < nv && n_tile > unit) n_tile -= n_tile % unit;  // whole waves of CTA tiles
+  if (n_tile < nv && n_tile > unit) {
+    n_tile -= n_tile % unit;  // whole waves of CTA tiles ...
+    const int64_t passes = (nv + n_tile - 1) / n_tile;  // ... and passes of equal size (no short last pass)
+    const int64_t bal = ((nv + passes - 1) / passes + unit - 1) / unit * unit;
+    if (bal < n_tile) n_tile = bal;
+  }
 
   // a3: conditioning embedding, once per batch (mocodad.py:157)
   if (m->Tc > 0) {
@@ -1056,7 +1091,7 @@ int mcd_score_windows_host(mcd_model* m, const float* h_data, int64_t B, int32_t
     m->host_best_floats = size_t(B);
   }
   const int64_t nv = int64_t(G) * B;
-  int64_t n_tile = tile_unit(m) * 64;
+  int64_t n_tile = tile_unit(m) * kDefaultWaves;
   if (n_tile > nv) n_tile = nv;
   const size_t need = carve_bytes(m, n_tile) + (align_floats(size_t(B) * m->E) + align_floats(size_t(nv))) * sizeof(float);
   if (need > m->host_ws_bytes) {

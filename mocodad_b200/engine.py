@@ -203,7 +203,7 @@ class ScoringEngine:
         if B == 0:
             return out
         nv = G * B
-        tile = min(nv, int(tile_windows) if tile_windows else 64 * self.tile_unit)
+        tile = min(nv, int(tile_windows) if tile_windows else 128 * self.tile_unit)
         ws = self._workspace(self.workspace_bytes(tile) + 4 * (B * self.E + nv) + 1024)
         with torch.cuda.device(self.device):
             check(self.lib.mcd_reverse_diffusion(
