@@ -48,7 +48,7 @@ constexpr int kTcLoadWarp = 13;    // the activation loader warp; warp 14 loads 
                                    // for blocks with a residual convolution
 constexpr int kTcThreads = 16 * 32;
 // Register budgets per warpgroup (setmaxnreg): the T-mix threads keep 96 weights + two accumulator sets in registers.
-constexpr int kRegsT = 208, kRegsA = 168, kRegsE = 88, kRegsS = 48;
+constexpr int kRegsT = 200, kRegsA = 152, kRegsE = 104, kRegsS = 56;
 static_assert(kRegsT + kRegsA + kRegsE + kRegsS <= 512, "one warp of each group shares an SM sub-partition (16K registers)");
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -135,18 +135,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
         "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float4 ldg_nc4(const float* p) {  // read-only global load, streaming
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
+// (no "memory" clobber: the kernel never reads what it stores, and a clobber would pin every shared-memory load of the
+//  epilogue behind the previous store)
 __device__ __forceinline__ void stg4(float* p, const float4 v) {
-  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
 }
 
 // shared-memory 16-byte load the compiler will not sink towards its use (keeps the software pipeline's lead)
@@ -339,15 +340,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
   __shared__ int trace_n;
   if (tid == 0) trace_n = 0;
   auto TRACE = [&](int role, int it, int ev) {
-    if (io.trace != nullptr && blockIdx.x == 0 && lane == 0) {
+    if (io.trace != nullptr && io.trace_cap > 0 && blockIdx.x == 0 && lane == 0) {  // trace_cap < 0: wait accounting only
       const int k = atomicAdd(&trace_n, 1);
       if (k < io.trace_cap) {
         io.trace[4 * k + 0] = role; io.trace[4 * k + 1] = it; io.trace[4 * k + 2] = ev; io.trace[4 * k + 3] = clock64();
       }
     }
   };
+  // wait accounting: cycles this thread spent in each of its (up to 4) barrier waits, reported at the end of the role
+  long long wacc[4] = {0, 0, 0, 0};
+  auto WAIT = [&](int slot, uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    wacc[slot] += clock64() - t0;
+  };
+  const long long role_t0 = clock64();
+  auto WAIT_REPORT = [&](int role) {  // records (role, 100 + slot, 0, cycles waited) and (role, 99, 0, cycles in the role)
+    if (io.trace != nullptr && blockIdx.x == 0 && lane == 0) {
+      for (int k = 0; k < 5; ++k) {
+        const int r = atomicAdd(&trace_n, 1);
+        if (r < (io.trace_cap < 0 ? -io.trace_cap : io.trace_cap)) {
+          io.trace[4 * r + 0] = role; io.trace[4 * r + 1] = k < 4 ? 100 + k : 99; io.trace[4 * r + 2] = 0;
+          io.trace[4 * r + 3] = k < 4 ? wacc[k] : clock64() - role_t0;
+        }
+      }
+    }
+  };
 #else
   auto TRACE = [](int, int, int) {};
+  auto WAIT = [&](int, uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); };
+  auto WAIT_REPORT = [](int) {};
 #endif
 
   // ---- once per CTA ----
@@ -399,9 +421,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
     for (int it = 0; it < npairs; ++it) {
       const int b = it % NXB, s = it & 1;
       if (warp == 0) TRACE(0, it, 0);
-      mbar_wait(BAR(BAR_X_FULL + b), uint32_t((it / NXB) & 1));
+      WAIT(0, BAR(BAR_X_FULL + b), uint32_t((it / NXB) & 1));
       if (warp == 0) TRACE(0, it, 1);
-      if (it >= 2) mbar_wait(BAR(BAR_Y1_EMPTY + s), uint32_t((it / 2 - 1) & 1));
+      if (it >= 2) WAIT(1, BAR(BAR_Y1_EMPTY + s), uint32_t((it / 2 - 1) & 1));
       if (warp == 0) TRACE(0, it, 2);
       if (active) {
         const float* sXc = sX + b * ARR;
@@ -453,6 +475,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       mbar_arrive(BAR(BAR_Y1_FULL + s));
       mbar_arrive(BAR(BAR_X_EMPTY + b));
     }
+    if (warp == 0) WAIT_REPORT(0);
   } else if (warp < 8) {
     // =============================== A-mix warps ===============================
     reg_inc<kRegsA>();
@@ -476,10 +499,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
     for (int it = 0; it < npairs; ++it) {
       const int s = it & 1;
       if (warp == 4) TRACE(1, it, 0);
-      mbar_wait(BAR(BAR_Y1_FULL + s), uint32_t((it / 2) & 1));
+      WAIT(0, BAR(BAR_Y1_FULL + s), uint32_t((it / 2) & 1));
       if (warp == 4) TRACE(1, it, 1);
       constexpr int NY2 = Cfg::NY2;  // Y2 / Y2lo buffer it % NY2 was last read by the MMAs of iteration it - NY2
-      if (it >= NY2) mbar_wait(BAR(BAR_MMA_DONE + ((it - NY2) & 1)), uint32_t(((it - NY2) / 2) & 1));
+      if (it >= NY2) WAIT(1, BAR(BAR_MMA_DONE + ((it - NY2) & 1)), uint32_t(((it - NY2) / 2) & 1));
       if (warp == 4) TRACE(1, it, 2);
       if (active) {
         const float* sY = sY1 + s * Y1ARR;
@@ -537,6 +560,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       if (warp == 4) TRACE(1, it, 4);
       mbar_arrive(BAR(BAR_OPS_FULL + s));
     }
+    if (warp == 4) WAIT_REPORT(1);
   } else if (warp >= kTcMmaWarp) {
     reg_dec<kRegsS>();
     if (warp == kTcMmaWarp) {
@@ -555,12 +579,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       const uint64_t bW = s ? dW_1 : dW_0;
       const uint32_t d0 = tmem + set * Cfg::ACC_COLS;
       TRACE(2, it, 0);
-      mbar_wait(BAR(BAR_W_FULL + s), uint32_t((it / 2) & 1));
-      if (chunk == 0 && ti >= 2) mbar_wait(BAR(BAR_ACC_EMPTY + set), uint32_t((ti / 2 - 1) & 1));  // set drained by the epilogue
+      WAIT(0, BAR(BAR_W_FULL + s), uint32_t((it / 2) & 1));
+      if (chunk == 0 && ti >= 2) WAIT(1, BAR(BAR_ACC_EMPTY + set), uint32_t((ti / 2 - 1) & 1));  // set drained by the epilogue
       if constexpr (RESCONV) {
         // residual 1x1 convolution of this chunk, straight from the landed X buffer: issued as soon as the lo part
         // exists, i.e. long before the mixes of the chunk finish, so the X ring slot is released early
-        mbar_wait(BAR(BAR_XLO_FULL + s), uint32_t((it / 2) & 1));
+        WAIT(2, BAR(BAR_XLO_FULL + s), uint32_t((it / 2) & 1));
         tc_fence_after();
         const uint64_t xHi = dX_0 + uint64_t(b) * ARR16, xLo = dXlo_0 + uint64_t(it % Cfg::NXLO) * ARR16;
         if (elect_one()) {
@@ -581,7 +605,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
         __syncwarp();
       }
       TRACE(2, it, 1);
-      mbar_wait(BAR(BAR_OPS_FULL + s), uint32_t((it / 2) & 1));
+      WAIT(3, BAR(BAR_OPS_FULL + s), uint32_t((it / 2) & 1));
       TRACE(2, it, 2);
       tc_fence_after();
       const uint64_t aHi = dY2_0 + uint64_t(it % Cfg::NY2) * ARR16, aLo = dY2lo_0 + uint64_t(it % Cfg::NY2) * ARR16;
@@ -604,6 +628,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       __syncwarp();
       TRACE(2, it, 3);
     }
+    WAIT_REPORT(2);
     } else if (warp == kTcLoadWarp) {
     // =============================== activation loader warp ===============================
     for (int it = 0; it < npairs; ++it) {
@@ -611,7 +636,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       const int64_t tile = blockIdx.x + int64_t(ti) * gridDim.x;
       const int b = it % NXB;
       TRACE(3, it, 0);
-      if (it >= NXB) mbar_wait(BAR(BAR_X_EMPTY + b), uint32_t((it / NXB - 1) & 1));
+      if (it >= NXB) WAIT(0, BAR(BAR_X_EMPTY + b), uint32_t((it / NXB - 1) & 1));
       TRACE(3, it, 1);
       // one bulk copy per (window, 4-channel plane): P x 16 contiguous bytes of the planar-4 source land as one
       // plane of the planar X buffer [c4][window][position] (rows = (window, position) are contiguous inside a
@@ -631,27 +656,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       TRACE(3, it, 2);
       __syncwarp();
     }
+    WAIT_REPORT(3);
     } else if (warp == kTcLoadWarp + 1) {
     // =============================== weight loader warp ===============================
     // its own warp, so that waiting for a free weight buffer (MMAs of iteration it-2) never delays the activations
     for (int it = 0; it < npairs; ++it) {
       const int chunk = it % NCHUNK, s = it & 1;
-      if (it >= 2) mbar_wait(BAR(BAR_MMA_DONE + s), uint32_t((it / 2 - 1) & 1));  // W[s] free again
+      if (it >= 2) WAIT(0, BAR(BAR_MMA_DONE + s), uint32_t((it / 2 - 1) & 1));  // W[s] free again
       if (lane == 0) {
         mbar_expect_tx(BAR(BAR_W_FULL + s), uint32_t(WCH * 4));
         bulk_g2s(smem_u32(sWc + s * WCH), wt.Bop + size_t(chunk) * WCH, uint32_t(WCH * 4), BAR(BAR_W_FULL + s));
       }
       __syncwarp();
     }
+    WAIT_REPORT(5);
     } else if constexpr (RESCONV) {
     // =============================== conversion warp (15) ===============================
     // tf32 lo part of the landed X chunk, same planar layout (an element-wise pass), for the residual convolution
     for (int it = 0; it < npairs; ++it) {
       constexpr int NXLO = Cfg::NXLO > 0 ? Cfg::NXLO : 1;
       const int b = it % NXB;
-      mbar_wait(BAR(BAR_X_FULL + b), uint32_t((it / NXB) & 1));
+      WAIT(0, BAR(BAR_X_FULL + b), uint32_t((it / NXB) & 1));
       // Xlo buffer it % NXLO was last read by the residual MMAs of iteration it - NXLO
-      if (it >= NXLO) mbar_wait(BAR(BAR_RES_DONE + ((it - NXLO) & 1)), uint32_t(((it - NXLO) / 2) & 1));
+      if (it >= NXLO) WAIT(1, BAR(BAR_RES_DONE + ((it - NXLO) & 1)), uint32_t(((it - NXLO) / 2) & 1));
       const float4* src = reinterpret_cast<const float4*>(sX + b * ARR);
       float4* dst = reinterpret_cast<float4*>(sXlo + (it % NXLO) * ARR);
       constexpr int NEL = ROWS * C4, U = 4;
@@ -667,6 +694,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor pipe
       mbar_arrive(BAR(BAR_XLO_FULL + (it & 1)));
     }
+    WAIT_REPORT(6);
     }
   } else {
     // =============================== epilogue warps ===============================
@@ -696,7 +724,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       }
       named_bar_sync(2, kTcEpilogue);
       if (warp == kTcEpiWarp0) TRACE(4, ti, 0);
-      mbar_wait(BAR(BAR_ACC_FULL + set), uint32_t((ti / 2) & 1));
+      WAIT(0, BAR(BAR_ACC_FULL + set), uint32_t((ti / 2) & 1));
       if (warp == kTcEpiWarp0) TRACE(4, ti, 1);
       tc_fence_after();
 #pragma unroll 1
@@ -716,17 +744,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
           }
           uint32_t acc[32];
           tmem_ld32(tmem + (uint32_t(q * 32) << 16) + uint32_t(set * Cfg::ACC_COLS + m * COUT + c0), acc);
+          // bias / embedding of the first two 4-channel groups travel while the TMEM load is in flight; the rest is
+          // fetched two groups ahead (shared-memory latency is ~100 cycles with the mixes and the tensor pipe on the port)
+          const float4* bp = reinterpret_cast<const float4*>(sBias + c0);
+          const float4* ep = reinterpret_cast<const float4*>(embp + c0);
+          float4 b4[2] = {bp[0], bp[1]}, e4[2] = {ep[0], ep[1]};
+          tmem_ld_wait();
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bc = b4[j4 & 1], ec = e4[j4 & 1];
+            if (j4 + 2 < 8) { b4[j4 & 1] = bp[j4 + 2]; e4[j4 & 1] = ep[j4 + 2]; }
             float o[4];
-            const float4 b4 = *reinterpret_cast<const float4*>(sBias + c0 + j4 * 4);
-            const float4 e4 = *reinterpret_cast<const float4*>(embp + c0 + j4 * 4);
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-              float v = __uint_as_float(acc[j4 * 4 + jj]) + f4get(b4, jj);
+              float v = __uint_as_float(acc[j4 * 4 + jj]) + f4get(bc, jj);
               if constexpr (!RESCONV) v += f4get(xr[j4], jj);
               v = v > 0.f ? v : slope * v;
-              o[jj] = v + f4get(e4, jj);
+              o[jj] = v + f4get(ec, jj);
             }
             if (ok) stg4(io.out + act_off(w, (c0 >> 2) + j4, pp, COUT, P), make_float4(o[0], o[1], o[2], o[3]));
           }
@@ -736,6 +770,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       if (warp == kTcEpiWarp0) TRACE(4, ti, 2);
       mbar_arrive(BAR(BAR_ACC_EMPTY + set));
     }
+    if (warp == kTcEpiWarp0) WAIT_REPORT(4);
   }
 
   // ---- teardown ----
