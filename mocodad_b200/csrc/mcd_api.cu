@@ -70,6 +70,7 @@ enum Slot {
   SLOT_ENC0,                            // 4 ST_GCNN blocks of the conditioning encoder
   SLOT_BTLNK = SLOT_ENC0 + kNumEncBlocks,
   SLOT_TAP,
+  SLOT_EMB,                             // time / condition embedding of all tensor-core blocks (one launch per denoiser call)
   SLOT_COUNT
 };
 const char* kSlotNames[SLOT_COUNT] = {
@@ -77,7 +78,7 @@ const char* kSlotNames[SLOT_COUNT] = {
     "st_gcnnsd3.1",  "st_gcnnsu4.0", "st_gcnnsu4.1", "st_gcnnsu3.0", "st_gcnnsu3.1", "down1",
     "down2",         "up3",          "up2",          "ddpm_step",    "randn",        "window_loss",
     "best_worst",    "cond.enc0",    "cond.enc1",    "cond.enc2",    "cond.enc3",    "cond.btlnk",
-    "tap_transpose"};
+    "tap_transpose", "time_embedding"};
 
 constexpr int nw_for(int T, int V0) {  // windows per CTA tile: ~408 (frame,joint) rows at the widest level
   return (408 / (T * V0)) > 0 ? 408 / (T * V0) : 1;
@@ -116,7 +117,9 @@ struct mcd_model {
   const float* d_pos = nullptr;  // [N][E]
   std::vector<float> beta, alpha, alpha_hat;
   // per-window workspace (floats)
-  size_t ws_buf = 0, ws_d1 = 0, ws_d2 = 0, ws_x = 0;
+  size_t ws_buf = 0, ws_d1 = 0, ws_d2 = 0, ws_x = 0, ws_emb = 0;
+  EmbTable emb_table{};  // tensor-core denoiser blocks: embedding weights + column offsets in the emb rows
+  int emb_off[kNumUnetBlocks] = {};
   // measurement
   mutable std::atomic<int64_t> launches{0};
   mutable long long* d_trace = nullptr;  // debug timeline target for the next tensor-core block launch of slot trace_slot
@@ -362,11 +365,11 @@ int launch_resample(const mcd_model* m, int idx, const float* in, const float* s
 
 // ---- workspace -------------------------------------------------------------------------------
 struct Workspace {
-  float *bufA, *bufB, *d1, *d2, *x, *eps;
+  float *bufA, *bufB, *d1, *d2, *x, *eps, *emb;
 };
 size_t align_floats(size_t f) { return (f + 63) / 64 * 64; }  // 256-byte granules
 
-size_t per_window_floats(const mcd_model* m) { return 2 * m->ws_buf + m->ws_d1 + m->ws_d2 + 2 * m->ws_x; }
+size_t per_window_floats(const mcd_model* m) { return 2 * m->ws_buf + m->ws_d1 + m->ws_d2 + 2 * m->ws_x + m->ws_emb; }
 
 Workspace carve(const mcd_model* m, float* base, int64_t n) {
   Workspace w;
@@ -376,12 +379,13 @@ Workspace carve(const mcd_model* m, float* base, int64_t n) {
   w.d1 = base + o; o += align_floats(m->ws_d1 * n);
   w.d2 = base + o; o += align_floats(m->ws_d2 * n);
   w.x = base + o; o += align_floats(m->ws_x * n);
-  w.eps = base + o;
+  w.eps = base + o; o += align_floats(m->ws_x * n);
+  w.emb = base + o;
   return w;
 }
 size_t carve_bytes(const mcd_model* m, int64_t n) {
   return sizeof(float) * (2 * align_floats(m->ws_buf * n) + align_floats(m->ws_d1 * n) + align_floats(m->ws_d2 * n) +
-                          2 * align_floats(m->ws_x * n));
+                          2 * align_floats(m->ws_x * n) + align_floats(m->ws_emb * n));
 }
 
 // ---- the denoiser ----------------------------------------------------------------------------
@@ -410,6 +414,7 @@ int unet_forward_impl(const mcd_model* m, const float* d_x, int64_t n, int t, co
     io.in = in;
     io.out = out;
     io.in_sn = 0; io.in_sc = 0; io.in_t0 = 0; io.xres = nullptr;
+    io.emb_off = m->emb_off[idx];
     if (idx == 0) { io.in_sn = int64_t(2) * T * 17; io.in_sc = T * 17; }
     if (idx == kNumUnetBlocks - 1) {
       io.xres = (tap != nullptr && strcmp(tap, kUnetBlocks[idx].name) == 0) ? nullptr : d_x;
@@ -427,6 +432,18 @@ int unet_forward_impl(const mcd_model* m, const float* d_x, int64_t n, int t, co
     return launch_resample(m, idx, in, skip, out, n, C, s);
   };
 
+  if (m->use_tc) {  // Linear(SiLU(pos(t) + cond)) of the tensor-core blocks, all windows (stsgcn.py:112-114)
+    const EmbTable& tb = m->emb_table;
+    const size_t smem = (size_t(m->E) * tb.total + tb.total + size_t(kEmbWin) * m->E) * sizeof(float);
+    const int grid = grid_for(n, kEmbWin, m->num_sms, 2);
+    {
+      LaunchScope ls(m, SLOT_EMB, n, s);
+      time_embedding_kernel<<<grid, kEmbThreads, smem, s>>>(tb, io.pos, io.cond, io.condB, io.w0, n, m->E, ws.emb);
+    }
+    MCD_TRY(check_launch("time_embedding"));
+    io.emb = ws.emb;
+    io.emb_stride = tb.total;
+  }
   // models/stsae/stsae_unet.py:182-219 (_downscale), :365-403 (_upscale)
   MCD_TRY(block(0, d_x, ws.bufA));
   MCD_TRY(block(1, ws.bufA, ws.bufB));
@@ -823,6 +840,8 @@ int mcd_model_create(const mcd_config* cfg, mcd_model** out) {
   m->ws_d1 = size_t(32) * T * 17;
   m->ws_d2 = size_t(64) * T * 12;
   m->ws_x = size_t(2) * T * 17;
+  m->ws_emb = 0;
+  for (int i = 1; i + 1 < kNumUnetBlocks; ++i) m->ws_emb += kUnetBlocks[i].cout;  // blocks 1..9 run on the tensor-core kernel
   *out = m;
   return MCD_OK;
 }
@@ -902,6 +921,20 @@ int mcd_model_finalize(mcd_model* m) {
   m->arena_floats = ar.h.size();
   CUDA_TRY(cudaMemcpy(m->d_arena, ar.h.data(), ar.h.size() * sizeof(float), cudaMemcpyHostToDevice));
   for (int i = 0; i < kNumUnetBlocks; ++i) bind_block(&m->unet[i], uo[i], m->d_arena);
+  {
+    EmbTable& tb = m->emb_table;
+    tb.nblocks = 0; tb.total = 0;
+    for (int i = 1; i + 1 < kNumUnetBlocks; ++i) {
+      const int k = tb.nblocks++;
+      tb.WEt[k] = m->unet[i].w.WEt; tb.bE[k] = m->unet[i].w.bE;
+      tb.cout[k] = kUnetBlocks[i].cout; tb.off[k] = tb.total;
+      m->emb_off[i] = tb.total;
+      tb.total += kUnetBlocks[i].cout;
+    }
+    const size_t smem = (size_t(m->E) * tb.total + tb.total + size_t(kEmbWin) * m->E) * sizeof(float);
+    if (smem > 200 * 1024) return fail(MCD_ERR_UNSUPPORTED, "embedding_dim %d too large for the time-embedding kernel", m->E);
+    CUDA_TRY(cudaFuncSetAttribute(time_embedding_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  }
   for (int i = 0; i < kNumResample; ++i) { m->rs[i].W = m->d_arena + rsW[i]; m->rs[i].b = m->d_arena + rsb[i]; }
   if (m->Tc > 0) {
     for (int i = 0; i < kNumEncBlocks; ++i) bind_block(&m->enc[i], eo[i], m->d_arena);
@@ -1032,7 +1065,7 @@ int mcd_reverse_diffusion(const mcd_model* m, const float* d_data, int64_t B, in
   float* tile_base = base + fixed;
   const size_t tile_bytes = ws_bytes - fixed * sizeof(float);
   // largest n with carve_bytes(n) <= tile_bytes (carve_bytes is monotone; per-buffer rounding costs < 6 granules)
-  int64_t n_tile = int64_t((tile_bytes - 6 * 256) / (per_window_floats(m) * sizeof(float)));
+  int64_t n_tile = int64_t((tile_bytes - 7 * 256) / (per_window_floats(m) * sizeof(float)));
   while (n_tile > 1 && carve_bytes(m, n_tile) > tile_bytes) --n_tile;
   if (n_tile < 1) n_tile = 1;
   if (n_tile > nv) n_tile = nv;
@@ -1195,6 +1228,9 @@ int mcd_profile_slot_cost(const mcd_model* m, int slot, double* bytes_per_window
   } else if (slot == SLOT_BTLNK) {
     bytes = 4.0 * (m->cfg.cond_h_dim * m->Tc * 17 + m->E);
     flops = 2.0 * m->cfg.cond_h_dim * m->Tc * 17 * m->E;
+  } else if (slot == SLOT_EMB) {
+    bytes = 4.0 * (m->E + m->ws_emb);
+    flops = 2.0 * m->E * m->ws_emb;
   }
   if (bytes_per_window) *bytes_per_window = bytes;
   if (flops_per_window) *flops_per_window = flops;

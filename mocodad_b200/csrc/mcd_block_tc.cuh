@@ -228,6 +228,7 @@ struct TcCfg {
   static constexpr int C4 = KC / 4;
   static constexpr bool RESCONV = CIN != COUT;
   static constexpr int NPART = RESCONV ? 4 : 2;  // weight operand parts per chunk: W hi, W lo [, Wr hi, Wr lo]
+  static constexpr bool RES_AHEAD = true;        // residual MMAs one chunk ahead of the convolution MMAs (see the MMA warp)
   static constexpr int VP = (V + 3) / 4 * 4;
   static constexpr int TP4 = (T + 3) / 4 * 4;
   static constexpr int TMS = T * TP4 + 4;
@@ -267,7 +268,7 @@ struct TcCfg {
   // Buffer counts by what fits into 227 KB: the X ring (planar [c4][window][position] 16-byte elements) is 3 deep where
   // possible -- the refill of a slot (release -> bulk copy issue -> ~1.5 k cycles of latency) then hides behind two mix
   // iterations instead of one; the widest tiles (V=17 with a residual convolution) fall back to single Xlo / Y2 buffers.
-  static constexpr int SM_MISC = 2 * Y1ARR + 2 * WCH + COUT + NW * COUT + NW * kMaxE;
+  static constexpr int SM_MISC = 2 * Y1ARR + 2 * WCH + COUT + NW * COUT;
   static constexpr bool tc_fits(int arrays) { return size_t(SM_MISC + arrays * ARR) * sizeof(float) + 1024 <= 227 * 1024; }
   static constexpr int NXLO = !RESCONV ? 0 : (tc_fits(2 + 2 + 4) ? 2 : 1);
   static constexpr int NY2 = tc_fits(2 + NXLO + 4) ? 2 : 1;
@@ -281,8 +282,7 @@ struct TcCfg {
   static constexpr int SM_WC = SM_Y2LO + NY2 * ARR;           // 2; also absorbs the last tile's over-read
   static constexpr int SM_BIAS = SM_WC + 2 * WCH;
   static constexpr int SM_EMB = SM_BIAS + COUT;
-  static constexpr int SM_S = SM_EMB + NW * COUT;
-  static constexpr int SM_TOTAL = SM_S + NW * kMaxE;
+  static constexpr int SM_TOTAL = SM_EMB + NW * COUT;
   static_assert((MT * 128 - ROWS) * 16 <= 2 * WCH, "over-read of the last MMA tile must stay inside the allocation");
   static constexpr size_t SMEM_BYTES = size_t(SM_TOTAL) * sizeof(float) + 1024;  // + alignment slack
 };
@@ -322,7 +322,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
   float* sWc = smem + Cfg::SM_WC;
   float* sBias = smem + Cfg::SM_BIAS;
   float* sEmb = smem + Cfg::SM_EMB;
-  float* sS = smem + Cfg::SM_S;
   __shared__ __align__(8) uint64_t bars[BAR_COUNT];
   __shared__ uint32_t tmem_slot;
 
@@ -355,6 +354,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
     wacc[slot] += clock64() - t0;
   };
   const long long role_t0 = clock64();
+  auto PHASE = [&](int slot, long long t0) { wacc[slot] += clock64() - t0; };  // free-form phase timer (epilogue)
   auto WAIT_REPORT = [&](int role) {  // records (role, 100 + slot, 0, cycles waited) and (role, 99, 0, cycles in the role)
     if (io.trace != nullptr && blockIdx.x == 0 && lane == 0) {
       for (int k = 0; k < 5; ++k) {
@@ -370,6 +370,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
   auto TRACE = [](int, int, int) {};
   auto WAIT = [&](int, uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); };
   auto WAIT_REPORT = [](int) {};
+  auto PHASE = [](int, long long) {};
+#endif
+#if MCD_TC_TRACE
+#define MCD_CLOCK() clock64()
+#else
+#define MCD_CLOCK() 0ll
 #endif
 
   // ---- once per CTA ----
@@ -573,36 +579,52 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
     const uint64_t dX_0 = umma_desc_planar(smem_u32(sX), ROWS * 16), dXlo_0 = umma_desc_planar(smem_u32(sXlo), ROWS * 16);
     constexpr uint64_t ARR16 = (uint64_t(ARR) * 4) >> 4;   // one operand array, in descriptor address units (16 bytes)
     constexpr uint64_t PART = (COUT * 64) >> 4;            // one weight part, in descriptor address units
+    // residual 1x1 convolution of iteration j, straight from the landed X buffer: issued as soon as the lo part exists,
+    // i.e. long before the mixes of the chunk finish, so the X ring slot is released early
+    auto issue_res = [&](int j) {
+      const int tj = j / NCHUNK, cj = j - tj * NCHUNK;
+      const int set = tj & 1, s = j & 1, b = j % NXB;
+      const uint64_t bW = s ? dW_1 : dW_0;
+      const uint32_t d0 = tmem + set * Cfg::ACC_COLS;
+      WAIT(0, BAR(BAR_W_FULL + s), uint32_t((j / 2) & 1));
+      if (cj == 0 && tj >= 2) WAIT(1, BAR(BAR_ACC_EMPTY + set), uint32_t((tj / 2 - 1) & 1));  // set drained by the epilogue
+      WAIT(2, BAR(BAR_XLO_FULL + s), uint32_t((j / 2) & 1));
+      tc_fence_after();
+      const uint64_t xHi = dX_0 + uint64_t(b) * ARR16, xLo = dXlo_0 + uint64_t(j % (Cfg::NXLO > 0 ? Cfg::NXLO : 1)) * ARR16;
+      if (elect_one()) {
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const uint32_t d = d0 + m * COUT;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {  // two K=8 steps per 16-channel chunk: c4 planes (2h, 2h+1)
+            const uint64_t ao = uint64_t((m * 128 * 16 + h * 2 * ROWS * 16) >> 4), bo = uint64_t((h * 32) >> 4);
+            umma_tf32(d, xLo + ao, bW + 2 * PART + bo, idesc, (cj > 0 || h > 0) ? 1u : 0u);
+            umma_tf32(d, xHi + ao, bW + 3 * PART + bo, idesc, 1u);
+            umma_tf32(d, xHi + ao, bW + 2 * PART + bo, idesc, 1u);
+          }
+        }
+        umma_commit(BAR(BAR_RES_DONE + s));  // Xlo buffer free again
+        umma_commit(BAR(BAR_X_EMPTY + b));   // ... and the X ring slot (together with the T-warps' arrivals)
+      }
+      __syncwarp();
+    };
+    int res_issued = 0;  // residual MMAs are in the pipe for iterations < res_issued
     for (int it = 0; it < npairs; ++it) {
       const int ti = it / NCHUNK, chunk = it - ti * NCHUNK;
-      const int set = ti & 1, s = it & 1, b = it % NXB;
+      const int set = ti & 1, s = it & 1;
       const uint64_t bW = s ? dW_1 : dW_0;
       const uint32_t d0 = tmem + set * Cfg::ACC_COLS;
       TRACE(2, it, 0);
-      WAIT(0, BAR(BAR_W_FULL + s), uint32_t((it / 2) & 1));
-      if (chunk == 0 && ti >= 2) WAIT(1, BAR(BAR_ACC_EMPTY + set), uint32_t((ti / 2 - 1) & 1));  // set drained by the epilogue
       if constexpr (RESCONV) {
-        // residual 1x1 convolution of this chunk, straight from the landed X buffer: issued as soon as the lo part
-        // exists, i.e. long before the mixes of the chunk finish, so the X ring slot is released early
-        WAIT(2, BAR(BAR_XLO_FULL + s), uint32_t((it / 2) & 1));
-        tc_fence_after();
-        const uint64_t xHi = dX_0 + uint64_t(b) * ARR16, xLo = dXlo_0 + uint64_t(it % Cfg::NXLO) * ARR16;
-        if (elect_one()) {
-#pragma unroll
-          for (int m = 0; m < MT; ++m) {
-            const uint32_t d = d0 + m * COUT;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {  // two K=8 steps per 16-channel chunk: c4 planes (2h, 2h+1)
-              const uint64_t ao = uint64_t((m * 128 * 16 + h * 2 * ROWS * 16) >> 4), bo = uint64_t((h * 32) >> 4);
-              umma_tf32(d, xLo + ao, bW + 2 * PART + bo, idesc, (chunk > 0 || h > 0) ? 1u : 0u);
-              umma_tf32(d, xHi + ao, bW + 3 * PART + bo, idesc, 1u);
-              umma_tf32(d, xHi + ao, bW + 2 * PART + bo, idesc, 1u);
-            }
-          }
-          umma_commit(BAR(BAR_RES_DONE + s));  // Xlo[s] free again
-          umma_commit(BAR(BAR_X_EMPTY + b));   // ... and the X ring slot (together with the T-warps' arrivals)
-        }
-        __syncwarp();
+        if (res_issued <= it) { issue_res(it); res_issued = it + 1; }
+        // One chunk ahead inside a tile: the residual MMAs of chunk c+1 enter the pipe before the (later) convolution
+        // MMAs of chunk c and free their X slot a whole iteration earlier.  Never across tiles (that would make this
+        // tile's last convolution wait for the epilogue of the previous tile), and unconditionally inside one, so
+        // the accumulation order -- hence every bit of the result -- does not depend on timing.
+        if (Cfg::RES_AHEAD && chunk + 1 < NCHUNK) { issue_res(it + 1); res_issued = it + 2; }
+      } else {
+        WAIT(0, BAR(BAR_W_FULL + s), uint32_t((it / 2) & 1));
+        if (chunk == 0 && ti >= 2) WAIT(1, BAR(BAR_ACC_EMPTY + set), uint32_t((ti / 2 - 1) & 1));  // set drained by the epilogue
       }
       TRACE(2, it, 1);
       WAIT(3, BAR(BAR_OPS_FULL + s), uint32_t((it / 2) & 1));
@@ -703,26 +725,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
     const float slope = wt.prelu;
     const int q = warp & 3;  // TMEM lane quarter this warp may access (warps 8-11 -> quarters 0-3)
     const int etid = tid - kTcEpiWarp0 * 32;
-    const int E = io.E;
+    // Linear(SiLU(pos + cond)) of the tile's windows comes precomputed (time_embedding_kernel); each thread carries its
+    // share of the NEXT tile's values in registers so the global latency never sits on the per-tile critical path
+    constexpr int EPER = (NW * COUT + kTcEpilogue - 1) / kTcEpilogue;
+    float epre[EPER];
+    auto load_emb = [&](int64_t tl) {
+#pragma unroll
+      for (int k = 0; k < EPER; ++k) {
+        const int i = etid + k * kTcEpilogue;
+        const int wl = i / COUT, co = i - wl * COUT;
+        const int64_t w = tl * NW + wl;
+        epre[k] = (i < NW * COUT && w < io.n) ? __ldg(io.emb + w * io.emb_stride + io.emb_off + co) : 0.f;
+      }
+    };
+    load_emb(blockIdx.x);
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int64_t tile = blockIdx.x + int64_t(ti) * gridDim.x;
       const int set = ti & 1;
+      const long long t_emb = MCD_CLOCK();
       named_bar_sync(2, kTcEpilogue);  // everyone is done with the previous tile's sEmb
-      for (int i = etid; i < NW * E; i += kTcEpilogue) {
-        const int wl = i / E, j = i - wl * E;
-        const int64_t w = tile * NW + wl;
-        float v = __ldg(io.pos + j);
-        if (io.cond != nullptr && w < io.n) v += __ldg(io.cond + ((io.w0 + w) % io.condB) * E + j);
-        sS[wl * kMaxE + j] = v / (1.0f + expf(-v));  // SiLU
-      }
+#pragma unroll
+      for (int k = 0; k < EPER; ++k)
+        if (etid + k * kTcEpilogue < NW * COUT) sEmb[etid + k * kTcEpilogue] = epre[k];
       named_bar_sync(2, kTcEpilogue);
-      for (int i = etid; i < NW * COUT; i += kTcEpilogue) {
-        const int wl = i / COUT, co = i - wl * COUT;
-        float e = __ldg(wt.bE + co);
-        for (int j = 0; j < E; ++j) e = fmaf(__ldg(wt.WEt + j * COUT + co), sS[wl * kMaxE + j], e);
-        sEmb[i] = e;
-      }
-      named_bar_sync(2, kTcEpilogue);
+      if (ti + 1 < my_tiles) load_emb(tile + gridDim.x);  // the next tile's values travel during this tile's stores
+      PHASE(1, t_emb);
       if (warp == kTcEpiWarp0) TRACE(4, ti, 0);
       WAIT(0, BAR(BAR_ACC_FULL + set), uint32_t((ti / 2) & 1));
       if (warp == kTcEpiWarp0) TRACE(4, ti, 1);
@@ -743,6 +770,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
             for (int j4 = 0; j4 < 8; ++j4) xr[j4] = ldg_nc4(io.in + (ok ? act_off(w, (c0 >> 2) + j4, pp, CIN, P) : 0));
           }
           uint32_t acc[32];
+          const long long t_ld = MCD_CLOCK();
           tmem_ld32(tmem + (uint32_t(q * 32) << 16) + uint32_t(set * Cfg::ACC_COLS + m * COUT + c0), acc);
           // bias / embedding of the first two 4-channel groups travel while the TMEM load is in flight; the rest is
           // fetched two groups ahead (shared-memory latency is ~100 cycles with the mixes and the tensor pipe on the port)
@@ -750,6 +778,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
           const float4* ep = reinterpret_cast<const float4*>(embp + c0);
           float4 b4[2] = {bp[0], bp[1]}, e4[2] = {ep[0], ep[1]};
           tmem_ld_wait();
+          PHASE(2, t_ld);
+          const long long t_st = MCD_CLOCK();
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 bc = b4[j4 & 1], ec = e4[j4 & 1];
@@ -764,6 +794,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
             }
             if (ok) stg4(io.out + act_off(w, (c0 >> 2) + j4, pp, COUT, P), make_float4(o[0], o[1], o[2], o[3]));
           }
+          PHASE(3, t_st);
         }
       }
       tc_fence_before();  // accumulator reads ordered before the release of the set

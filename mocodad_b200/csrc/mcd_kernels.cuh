@@ -104,6 +104,10 @@ struct BlockIO {
   long long* trace;   // debug: CTA 0 records (role, pair, event, clock64) quadruples here (nullptr: off)
   int trace_cap;      // capacity in records
   int32_t E;
+  // tensor-core block kernel: time/condition embedding precomputed by time_embedding_kernel, [n][emb_stride] floats,
+  // this block's COUT values at column emb_off
+  const float* emb;
+  int32_t emb_stride, emb_off;
 };
 
 enum { IN_CL = 0, IN_CF = 1 };
@@ -535,6 +539,68 @@ __global__ void __launch_bounds__(kRsFrames) joint_resample_kernel(const float* 
       dst[i] = a;
     }
     __syncthreads();  // the next tile's copies overwrite the region
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Time / condition embedding of every tensor-core denoiser block, for all windows of a launch:
+//   emb[w][off_b + co] = bE_b[co] + sum_j WE_b[co][j] * SiLU(pos_t[j] + cond[w][j])        stsgcn.py:112-114 (emb_layer),
+//   temb = pos_encoding(t) + cond_emb                                                      stsae_unet.py:425-426
+// Computed once per denoiser call (0.03 % of its traffic) instead of once per tile inside the block kernels, where
+// the dependent global loads (condition row, then E rounds of weights) cost ~3.7 k cycles per tile on the epilogue
+// warps -- the bottleneck of the blocks with few channel chunks (wait accounting, tools/trace_block.py).
+// ------------------------------------------------------------------------------------------
+constexpr int kEmbBlocks = 9;    // denoiser blocks on the tensor-core kernel
+constexpr int kEmbThreads = 128;
+constexpr int kEmbWin = 8;       // windows per CTA step
+struct EmbTable {
+  const float* WEt[kEmbBlocks];  // [E][cout]
+  const float* bE[kEmbBlocks];   // [cout]
+  int32_t cout[kEmbBlocks], off[kEmbBlocks];
+  int32_t nblocks, total;        // total = sum of cout (row length of emb)
+};
+__global__ void __launch_bounds__(kEmbThreads) time_embedding_kernel(const EmbTable tb, const float* __restrict__ pos,
+                                                                      const float* __restrict__ cond, int64_t condB, int64_t w0,
+                                                                      int64_t n, int E, float* __restrict__ emb) {
+  extern __shared__ float emb_smem[];
+  float* sW = emb_smem;                       // [E][total]
+  float* sB = sW + size_t(E) * tb.total;      // [total]
+  float* sS = sB + tb.total;                  // [kEmbWin][E]
+  const int tid = threadIdx.x, total = tb.total;
+  for (int b = 0; b < tb.nblocks; ++b) {
+    const int co_n = tb.cout[b], off = tb.off[b];
+    for (int i = tid; i < E * co_n; i += kEmbThreads) {
+      const int j = i / co_n, co = i - j * co_n;
+      sW[j * total + off + co] = tb.WEt[b][i];
+    }
+    for (int i = tid; i < co_n; i += kEmbThreads) sB[off + i] = tb.bE[b][i];
+  }
+  __syncthreads();
+  const int64_t ngroups = (n + kEmbWin - 1) / kEmbWin;
+  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int64_t wbase = g * kEmbWin;
+    for (int i = tid; i < kEmbWin * E; i += kEmbThreads) {
+      const int wl = i / E, j = i - wl * E;
+      const int64_t w = wbase + wl;
+      float v = __ldg(pos + j);
+      if (cond != nullptr && w < n) v += __ldg(cond + ((w0 + w) % condB) * E + j);
+      sS[i] = v / (1.0f + expf(-v));  // SiLU
+    }
+    __syncthreads();
+    for (int o = tid; o < total; o += kEmbThreads) {
+      float e[kEmbWin];
+#pragma unroll
+      for (int wl = 0; wl < kEmbWin; ++wl) e[wl] = sB[o];
+      for (int j = 0; j < E; ++j) {
+        const float k = sW[j * total + o];
+#pragma unroll
+        for (int wl = 0; wl < kEmbWin; ++wl) e[wl] = fmaf(k, sS[wl * E + j], e[wl]);
+      }
+#pragma unroll
+      for (int wl = 0; wl < kEmbWin; ++wl)
+        if (wbase + wl < n) emb[(wbase + wl) * total + o] = e[wl];
+    }
+    __syncthreads();
   }
 }
 

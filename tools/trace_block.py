@@ -25,7 +25,7 @@ torch.cuda.synchronize()
 r = rec.cpu()
 roles = {0: "T", 1: "A", 2: "MMA", 3: "LOAD", 4: "EPI", 5: "WLOAD", 6: "XLO"}
 waits = {0: ["x_full", "y1_empty"], 1: ["y1_full", "y2_free"], 2: ["w_full", "acc_empty", "xlo_full", "ops_full"], 3: ["x_empty"],
-         4: ["acc_full"], 5: ["w_free"], 6: ["x_full", "xlo_free"]}
+         4: ["acc_full", "emb phase", "tmem ld+wait", "math+store"], 5: ["w_free"], 6: ["x_full", "xlo_free"]}
 acc = r[(r[:, 1] >= 99) & (r[:, 1] < 104)]
 print(f"slot {slot} ({eng.lib.mcd_profile_slot_name(slot).decode()}), {n} windows: cycles CTA 0 spent waiting, by role")
 for role in sorted(roles):
