@@ -137,7 +137,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The wait names the loaded registers as in/out operands: every use of them is ordered after it by data dependence.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                 "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 
 __device__ __forceinline__ float4 ldg_nc4(const float* p) {  // read-only global load, streaming
   float4 v;
@@ -145,9 +154,10 @@ __device__ __forceinline__ float4 ldg_nc4(const float* p) {  // read-only global
   return v;
 }
 // (no "memory" clobber: the kernel never reads what it stores, and a clobber would pin every shared-memory load of the
-//  epilogue behind the previous store)
-__device__ __forceinline__ void stg4(float* p, const float4 v) {
-  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+//  epilogue behind the previous store; predicated, so that a row past the end of the tensor costs no branch)
+__device__ __forceinline__ void stg4_pred(float* p, const float4 v, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p st.global.v4.f32 [%0], {%1,%2,%3,%4};\n\t}\n" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w), "r"(int(pred)));
 }
 
 // shared-memory 16-byte load the compiler will not sink towards its use (keeps the software pipeline's lead)
@@ -765,9 +775,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
 #pragma unroll 1
         for (int c0 = 0; c0 < COUT; c0 += 32) {
           float4 xr[8];
+          const float* ip = io.in + (ok ? act_off(w, c0 >> 2, pp, CIN, P) : 0);
+          float* op = io.out + (ok ? act_off(w, c0 >> 2, pp, COUT, P) : 0);
           if constexpr (!RESCONV) {  // identity residual: issue the loads of this column group before touching TMEM
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) xr[j4] = ldg_nc4(io.in + (ok ? act_off(w, (c0 >> 2) + j4, pp, CIN, P) : 0));
+            for (int j4 = 0; j4 < 8; ++j4) xr[j4] = ldg_nc4(ip + j4 * P * 4);  // 4-channel planes are P elements apart
           }
           uint32_t acc[32];
           const long long t_ld = MCD_CLOCK();
@@ -777,7 +789,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
           const float4* bp = reinterpret_cast<const float4*>(sBias + c0);
           const float4* ep = reinterpret_cast<const float4*>(embp + c0);
           float4 b4[2] = {bp[0], bp[1]}, e4[2] = {ep[0], ep[1]};
-          tmem_ld_wait();
+          tmem_ld_wait(acc);
           PHASE(2, t_ld);
           const long long t_st = MCD_CLOCK();
 #pragma unroll
@@ -792,7 +804,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
               v = v > 0.f ? v : slope * v;
               o[jj] = v + f4get(ec, jj);
             }
-            if (ok) stg4(io.out + act_off(w, (c0 >> 2) + j4, pp, COUT, P), make_float4(o[0], o[1], o[2], o[3]));
+            stg4_pred(op + j4 * P * 4, make_float4(o[0], o[1], o[2], o[3]), ok);
           }
           PHASE(3, t_st);
         }
