@@ -1,6 +1,6 @@
 """Device-side timeline of one tensor-core block launch (debug aid): prints per-role event times for CTA 0.
 Needs the instrumented build: `python -m mocodad_b200._build --trace` (here, before gpurun; the .so travels).
-usage (on the GPU box): python tools/trace_block.py [slot=2] [n_windows=2368]"""
+usage (on the GPU box): python tools/trace_block.py [slot=2] [n_windows=2368] [events|waits] [seg_len=27]"""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -12,9 +12,11 @@ from mocodad_b200._lib import check
 slot = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 2368
 events = not (len(sys.argv) > 3 and sys.argv[3] == "waits")  # "waits": wait accounting only (no per-event perturbation)
-eng = ScoringEngine(seg_len=27, n_frames_cond=3, noise_steps=10, device="cuda:0")
-eng.load_state_dict(synth.synth_state_dict(synth.state_dict_spec(T=24, T_cond=3), seed=0))
-x = torch.randn(n, 2, 24, 17, device="cuda")
+seg_len = int(sys.argv[4]) if len(sys.argv) > 4 else 27
+T = seg_len - 3
+eng = ScoringEngine(seg_len=seg_len, n_frames_cond=3, noise_steps=10, device="cuda:0")
+eng.load_state_dict(synth.synth_state_dict(synth.state_dict_spec(T=T, T_cond=3), seed=0))
+x = torch.randn(n, 2, T, 17, device="cuda")
 cond = torch.randn(n, 16, device="cuda")
 eng.unet_forward(x, 5, cond)  # warm
 cap = 4096
