@@ -432,7 +432,7 @@ int unet_forward_impl(const mcd_model* m, const float* d_x, int64_t n, int t, co
     return launch_resample(m, idx, in, skip, out, n, C, s);
   };
 
-  if (m->use_tc) {  // Linear(SiLU(pos(t) + cond)) of the tensor-core blocks, all windows (stsgcn.py:112-114)
+  {  // Linear(SiLU(pos(t) + cond)) of all 11 blocks, all windows (stsgcn.py:112-114)
     const EmbTable& tb = m->emb_table;
     const size_t smem = (size_t(m->E) * tb.total + tb.total + size_t(kEmbWin) * m->E) * sizeof(float);
     const int grid = grid_for(n, kEmbWin, m->num_sms, 2);
@@ -841,7 +841,7 @@ int mcd_model_create(const mcd_config* cfg, mcd_model** out) {
   m->ws_d2 = size_t(64) * T * 12;
   m->ws_x = size_t(2) * T * 17;
   m->ws_emb = 0;
-  for (int i = 1; i + 1 < kNumUnetBlocks; ++i) m->ws_emb += kUnetBlocks[i].cout;  // blocks 1..9 run on the tensor-core kernel
+  for (int i = 0; i < kNumUnetBlocks; ++i) m->ws_emb += kUnetBlocks[i].cout;
   *out = m;
   return MCD_OK;
 }
@@ -924,7 +924,7 @@ int mcd_model_finalize(mcd_model* m) {
   {
     EmbTable& tb = m->emb_table;
     tb.nblocks = 0; tb.total = 0;
-    for (int i = 1; i + 1 < kNumUnetBlocks; ++i) {
+    for (int i = 0; i < kNumUnetBlocks; ++i) {
       const int k = tb.nblocks++;
       tb.WEt[k] = m->unet[i].w.WEt; tb.bE[k] = m->unet[i].w.bE;
       tb.cout[k] = kUnetBlocks[i].cout; tb.off[k] = tb.total;

@@ -96,17 +96,11 @@ __global__ void __launch_bounds__(Cfg::THREADS) edge_block_kernel(const BlockWei
       s0[0][tid] = 0.f;
       s0[1][tid] = 0.f;
     }
-    // time/condition embedding of the tile's windows (stsgcn.py:112-114)
+    // time/condition embedding of the tile's windows (stsgcn.py:112-114), precomputed by time_embedding_kernel
     for (int i = tid; i < NW * CE; i += Cfg::THREADS) {
       const int ewl = i / CE, co = i - ewl * CE;
       const int64_t ew = tile * NW + ewl;
-      float e = __ldg(wt.bE + co);
-      for (int j = 0; j < io.E; ++j) {
-        float v = __ldg(io.pos + j);
-        if (io.cond != nullptr && ew < io.n) v += __ldg(io.cond + ((io.w0 + ew) % io.condB) * io.E + j);
-        e = fmaf(__ldg(wt.WEt + j * CE + co), v / (1.0f + expf(-v)), e);
-      }
-      sEmb[ewl][co] = e;
+      sEmb[ewl][co] = ew < io.n ? __ldg(io.emb + ew * io.emb_stride + io.emb_off + co) : 0.f;
     }
     __syncthreads();
 

@@ -543,14 +543,14 @@ __global__ void __launch_bounds__(kRsFrames) joint_resample_kernel(const float* 
 }
 
 // ------------------------------------------------------------------------------------------
-// Time / condition embedding of every tensor-core denoiser block, for all windows of a launch:
+// Time / condition embedding of every denoiser block, for all windows of a launch:
 //   emb[w][off_b + co] = bE_b[co] + sum_j WE_b[co][j] * SiLU(pos_t[j] + cond[w][j])        stsgcn.py:112-114 (emb_layer),
 //   temb = pos_encoding(t) + cond_emb                                                      stsae_unet.py:425-426
 // Computed once per denoiser call (0.03 % of its traffic) instead of once per tile inside the block kernels, where
 // the dependent global loads (condition row, then E rounds of weights) cost ~3.7 k cycles per tile on the epilogue
 // warps -- the bottleneck of the blocks with few channel chunks (wait accounting, tools/trace_block.py).
 // ------------------------------------------------------------------------------------------
-constexpr int kEmbBlocks = 9;    // denoiser blocks on the tensor-core kernel
+constexpr int kEmbBlocks = 11;   // all ST_GCNN blocks of the denoiser
 constexpr int kEmbThreads = 128;
 constexpr int kEmbWin = 8;       // windows per CTA step
 struct EmbTable {
