@@ -37,6 +37,9 @@
 #ifndef MCD_TC_TRACE
 #define MCD_TC_TRACE 0
 #endif
+#ifndef MCD_EXP_SKIP_A
+#define MCD_EXP_SKIP_A 0  // experiment only (wrong results): the A-mix warps skip their arithmetic
+#endif
 
 namespace mcd {
 
@@ -520,7 +523,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       constexpr int NY2 = Cfg::NY2;  // Y2 / Y2lo buffer it % NY2 was last read by the MMAs of iteration it - NY2
       if (it >= NY2) WAIT(1, BAR(BAR_MMA_DONE + ((it - NY2) & 1)), uint32_t(((it - NY2) / 2) & 1));
       if (warp == 4) TRACE(1, it, 2);
-      if (active) {
+      if (active && !MCD_EXP_SKIP_A) {
         const float* sY = sY1 + s * Y1ARR;
         float* sZ = sY2 + (it % NY2) * ARR;
         float* sZlo = sY2lo + (it % NY2) * ARR;
