@@ -54,8 +54,13 @@ __global__ void __launch_bounds__(128, 1) k(const float* wsrc, float* out, int p
 #pragma unroll
         for (int q = 0; q < QG; ++q) {
           const float2 ww = make_float2(wT[t][q], wT[t][q]);
-          a[0][q] = __ffma2_rn(xl, ww, a[0][q]);
-          a[1][q] = __ffma2_rn(xh, ww, a[1][q]);
+          if (MODE == 2) {  // plain FFMA: four scalar fused multiply-adds per (frame, output frame)
+            a[0][q].x = fmaf(xl.x, ww.x, a[0][q].x); a[0][q].y = fmaf(xl.y, ww.x, a[0][q].y);
+            a[1][q].x = fmaf(xh.x, ww.x, a[1][q].x); a[1][q].y = fmaf(xh.y, ww.x, a[1][q].y);
+          } else {
+            a[0][q] = __ffma2_rn(xl, ww, a[0][q]);
+            a[1][q] = __ffma2_rn(xh, ww, a[1][q]);
+          }
         }
       }
     }
@@ -162,6 +167,8 @@ void run2(const char* what) {
 int main() {
   run2<24, 12, 3, 3>("two groups per pass (V=12)");
   run2<24, 17, 4, 3>("two groups per pass (V=17)");
+  run<24, 12, 3, 6, 2>("plain FFMA (V=12)");
+  run<24, 17, 4, 6, 2>("plain FFMA (V=17)");
   run<24, 12, 3, 6, 0>("kernel loop (V=12)");
   run<24, 12, 3, 6, 1>("no shared loads (V=12)");
   run<24, 17, 4, 6, 0>("kernel loop (V=17)");
