@@ -51,10 +51,24 @@ __global__ void __launch_bounds__(128, 1) k(const float* wsrc, float* out, int p
       for (int i = 0; i < TB; ++i) {
         const int t = tb + i;
         const float2 xl = make_float2(xc[i].x, xc[i].y), xh = make_float2(xc[i].z, xc[i].w);
+        if (MODE == 3) {
+          // accumulator a[c>>1][(c&1)*(QG/2) + qp] holds outputs (q=2qp, 2qp+1) of channel c
+          const float xs[4] = {xc[i].x, xc[i].y, xc[i].z, xc[i].w};
+#pragma unroll
+          for (int qp = 0; qp < QG / 2; ++qp) {
+            const float2 wp = make_float2(wT[t][2 * qp], wT[t][2 * qp + 1]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float2& acc = a[c >> 1][(c & 1) * (QG / 2) + qp];
+              acc = __ffma2_rn(wp, make_float2(xs[c], xs[c]), acc);
+            }
+          }
+        }
 #pragma unroll
         for (int q = 0; q < QG; ++q) {
           const float2 ww = make_float2(wT[t][q], wT[t][q]);
-          if (MODE == 2) {  // plain FFMA: four scalar fused multiply-adds per (frame, output frame)
+          if (MODE == 3) {  // weights as (q, q+1) register pairs, activations as broadcast scalars (QG even): handled below
+          } else if (MODE == 2) {  // plain FFMA: four scalar fused multiply-adds per (frame, output frame)
             a[0][q].x = fmaf(xl.x, ww.x, a[0][q].x); a[0][q].y = fmaf(xl.y, ww.x, a[0][q].y);
             a[1][q].x = fmaf(xh.x, ww.x, a[1][q].x); a[1][q].y = fmaf(xh.y, ww.x, a[1][q].y);
           } else {
@@ -167,6 +181,8 @@ void run2(const char* what) {
 int main() {
   run2<24, 12, 3, 3>("two groups per pass (V=12)");
   run2<24, 17, 4, 3>("two groups per pass (V=17)");
+  run<24, 17, 4, 6, 3>("weight pairs x scalar act (V=17)");
+  run<24, 10, 4, 6, 3>("weight pairs x scalar act (V=10)");
   run<24, 12, 3, 6, 2>("plain FFMA (V=12)");
   run<24, 17, 4, 6, 2>("plain FFMA (V=17)");
   run<24, 12, 3, 6, 0>("kernel loop (V=12)");
