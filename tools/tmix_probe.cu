@@ -10,12 +10,12 @@ __device__ __forceinline__ float4 lds4_early(const float* p) {
   return v;
 }
 template <int T, int V, int QG, int TB, int MODE>  // MODE 0: as in the kernel; 1: loads replaced by register moves
-__global__ void __launch_bounds__(128, 1) k(const float* wsrc, float* out, int passes, long long* cyc) {
+__global__ void __launch_bounds__(256, 1) k(const float* wsrc, float* out, int passes, long long* cyc) {
   extern __shared__ float sm[];
   constexpr int P = T * V, NQG = (T + QG - 1) / QG;
   float* sX = sm;                 // [4 c4][P] float4
   float* sY = sm + 4 * P * 4;     // output area
-  for (int i = threadIdx.x; i < 4 * P * 4; i += 128) sX[i] = 0.001f * (i % 97);
+  for (int i = threadIdx.x; i < 4 * P * 4; i += blockDim.x) sX[i] = 0.001f * (i % 97);
   __syncthreads();
   const int tid = threadIdx.x;
   const int rem = tid % (V * NQG) ;
@@ -87,14 +87,14 @@ __global__ void __launch_bounds__(128, 1) k(const float* wsrc, float* out, int p
   if (passes < 0) out[tid] = sY[tid];
 }
 template <int T, int V, int QG, int TB, int MODE>
-void run(const char* what) {
+void run(const char* what, int threads = 128) {
   float *w, *o; long long* c;
   cudaMalloc(&w, V * T * T * 4); cudaMemset(w, 0, V * T * T * 4); cudaMalloc(&o, 4096); cudaMalloc(&c, 8);
   constexpr int P = T * V;
   const size_t smem = (4 * P * 4 + 4 * QG * 136 * 4) * 4;
   cudaFuncSetAttribute(k<T, V, QG, TB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int passes = 4000;
-  k<T, V, QG, TB, MODE><<<148, 128, smem>>>(w, o, passes, c);
+  k<T, V, QG, TB, MODE><<<148, threads, smem>>>(w, o, passes, c);
   cudaError_t e = cudaDeviceSynchronize();
   long long cyc; cudaMemcpy(&cyc, c, 8, cudaMemcpyDeviceToHost);
   printf("%-34s T=%d V=%d QG=%d TB=%d: %7.1f cycles per pass, %.2f cycles per FFMA2 (%s)\n", what, T, V, QG, TB, double(cyc) / passes,
@@ -186,6 +186,8 @@ int main() {
   run<24, 12, 3, 6, 2>("plain FFMA (V=12)");
   run<24, 17, 4, 6, 2>("plain FFMA (V=17)");
   run<24, 12, 3, 6, 0>("kernel loop (V=12)");
+  run<24, 12, 3, 6, 0>("2 warps per sub-partition (V=12)", 256);
+  run<24, 17, 4, 6, 0>("2 warps per sub-partition (V=17)", 256);
   run<24, 12, 3, 6, 1>("no shared loads (V=12)");
   run<24, 17, 4, 6, 0>("kernel loop (V=17)");
   run<24, 17, 4, 6, 1>("no shared loads (V=17)");
