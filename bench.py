@@ -237,6 +237,25 @@ def run_b200(a):
     e2e_value = world * B / e2e_s
     assert bool(torch.isfinite(scores).all())
 
+    # ---- row f1: dataset items (5 affine transforms per base window) built on the device ----------
+    from mocodad_b200.engine import pose_transform_matrices
+    mats = pose_transform_matrices(5)
+    n_base = (B + 4) // 5
+    base = data[:n_base].contiguous()
+    for _ in range(3):
+        eng.expand_transforms(base, mats, 0, min(B, 5 * n_base))
+    xe0, xe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    xe0.record()
+    for _ in range(20):
+        items = eng.expand_transforms(base, mats, 0, min(B, 5 * n_base))
+    xe1.record()
+    torch.cuda.synchronize(dev)
+    xf_s = xe0.elapsed_time(xe1) * 1e-3 / 20
+    ingest = {"kernel": "expand_transforms", "items_per_s": items.shape[0] / xf_s,
+              "GBps": round(2 * items.numel() * 4 / xf_s / 1e9, 1),
+              "note": "dataset item = affine transform idx//N of base window idx%N (utils/dataset.py:67-76), built on the "
+                      "device from base windows uploaded once; launch-latency-bound at this batch size"}
+
     # ---- per-kernel device times (CUDA events around every launch, one extra step) -----------
     eng.profile_enable(True)
     step_device()
@@ -320,7 +339,7 @@ def run_b200(a):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": B * 4,
                     "ms_per_step": e2e_s * 1e3, "api": "mcd_score_windows_host (pinned host windows in, host scores out)"},
             "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "kernels": kernels}
+            "ingest": ingest, "kernels": kernels}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -137,6 +137,17 @@ MCD_API int mcd_ddpm_step(const mcd_model* m, float* d_x, const float* d_eps, co
 MCD_API int mcd_randn_windows(const mcd_model* m, float* d_x, int64_t n, uint64_t seed,
                       int64_t first_window, int32_t sample, int32_t noise_slot, void* stream);
 
+/* ---- f1 (first "next" row): dataset items = affine transforms of base windows ------
+ * mcd_pose_transform_matrix: rows 0-1 (6 floats, row-major) of ae_trans_list[index], index 0..4
+ * (utils/dataset_utils.py:255-270, 308-314) -- identity, flip, rot 90, rot 90 + flip, rot 45.
+ * mcd_expand_transforms: PoseDataset.__getitem__ (utils/dataset.py:67-76) + apply_pose_transform
+ * (utils/dataset_utils.py:273-290) on the device: item idx = first_item + i is transform idx / N of base
+ * window idx % N.  d_base [N,2,n_frames,V] (x, y), h_mats [num_transform][6], d_out [n_items,2,n_frames,V].
+ * The base windows cross PCIe once instead of num_transform times. */
+MCD_API int mcd_pose_transform_matrix(int32_t index, float* h_mat6);
+MCD_API int mcd_expand_transforms(const mcd_model* m, const float* d_base, int64_t N, const float* h_mats,
+                          int32_t num_transform, int64_t first_item, int64_t n_items, float* d_out, void* stream);
+
 /* ---- a11: per-window loss + aggregation, mocodad.py:454-520 --------------------------------
  * d_x0 [G*B,2,T,V] sample-major; d_data [B,2,n_frames,V] (the corrupt frames are the target).
  * d_losses [G,B] (may be NULL when G == 1) receives every sample's loss; d_best / d_worst [B]

@@ -53,6 +53,9 @@ SIGNATURES = {
                                 C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "mcd_randn_windows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_int64, C.c_int32, C.c_int32,
                                     C.c_void_p]),
+    "mcd_pose_transform_matrix": (C.c_int, [C.c_int32, c_float_p]),
+    "mcd_expand_transforms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_float_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p,
+                                        C.c_void_p]),
     "mcd_window_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
     "mcd_reverse_diffusion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_uint64,

@@ -71,6 +71,7 @@ enum Slot {
   SLOT_BTLNK = SLOT_ENC0 + kNumEncBlocks,
   SLOT_TAP,
   SLOT_EMB,                             // time / condition embedding of all tensor-core blocks (one launch per denoiser call)
+  SLOT_XFORM,                           // dataset-item expansion (affine transforms of the base windows)
   SLOT_COUNT
 };
 const char* kSlotNames[SLOT_COUNT] = {
@@ -78,7 +79,7 @@ const char* kSlotNames[SLOT_COUNT] = {
     "st_gcnnsd3.1",  "st_gcnnsu4.0", "st_gcnnsu4.1", "st_gcnnsu3.0", "st_gcnnsu3.1", "down1",
     "down2",         "up3",          "up2",          "ddpm_step",    "randn",        "window_loss",
     "best_worst",    "cond.enc0",    "cond.enc1",    "cond.enc2",    "cond.enc3",    "cond.btlnk",
-    "tap_transpose", "time_embedding"};
+    "tap_transpose", "time_embedding", "expand_transforms"};
 
 constexpr int nw_for(int T, int V0) {  // windows per CTA tile: ~408 (frame,joint) rows at the widest level
   return (408 / (T * V0)) > 0 ? 408 / (T * V0) : 1;
@@ -1023,6 +1024,56 @@ int mcd_randn_windows(const mcd_model* m, float* d_x, int64_t n, uint64_t seed, 
   return launch_randn(m, d_x, n, a, static_cast<cudaStream_t>(stream));
 }
 
+int mcd_pose_transform_matrix(int32_t index, float* h_mat6) {
+  // utils/dataset_utils.py:255-270 (get_aff_trans_mat) for the entries of ae_trans_list (:308-314): sx = sy = 1, tx = ty = 0;
+  // float64 cos/sin -> float32 matrices -> float32 products flip @ (rot @ trans_scale), like the reference's torch.matmul
+  static const struct { double rot; bool flip; } kList[5] = {{0, false}, {0, true}, {90, false}, {90, true}, {45, false}};
+  if (h_mat6 == nullptr || index < 0 || index >= 5) return fail(MCD_ERR_INVALID_ARG, "mcd_pose_transform_matrix: index %d outside ae_trans_list", index);
+  const double rad = kList[index].rot * (3.14159265358979323846 / 180.0);  // math.radians
+  const float c = float(std::cos(rad)), sn = float(std::sin(rad));
+  const float rot[3][3] = {{c, -sn, 0.f}, {sn, c, 0.f}, {0.f, 0.f, 1.f}};
+  const float ts[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+  float fl[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+  if (kList[index].flip) fl[0][0] = -1.f;
+  float a[3][3], r[3][3];
+  auto matmul = [](const float (*x)[3], const float (*y)[3], float (*z)[3]) {
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        float acc = 0.f;
+        for (int k = 0; k < 3; ++k) acc += x[i][k] * y[k][j];
+        z[i][j] = acc;
+      }
+  };
+  matmul(rot, ts, a);
+  matmul(fl, a, r);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 3; ++j) h_mat6[i * 3 + j] = r[i][j];
+  return MCD_OK;
+}
+
+int mcd_expand_transforms(const mcd_model* m, const float* d_base, int64_t N, const float* h_mats, int32_t num_transform,
+                          int64_t first_item, int64_t n_items, float* d_out, void* stream) {
+  MCD_TRY(check_ready(m));
+  if (d_base == nullptr || d_out == nullptr || h_mats == nullptr || N < 1 || n_items < 0 || first_item < 0)
+    return fail(MCD_ERR_INVALID_ARG, "mcd_expand_transforms: bad argument");
+  if (num_transform < 1 || num_transform > kMaxTransforms)
+    return fail(MCD_ERR_UNSUPPORTED, "mcd_expand_transforms: %d transforms (1..%d supported)", num_transform, kMaxTransforms);
+  if (first_item + n_items > int64_t(num_transform) * N)
+    return fail(MCD_ERR_INVALID_ARG, "mcd_expand_transforms: items [%lld, %lld) exceed the dataset of %d x %lld items", (long long)first_item,
+                (long long)(first_item + n_items), num_transform, (long long)N);
+  if (n_items == 0) return MCD_OK;
+  TransformTable tb{};
+  for (int t = 0; t < num_transform; ++t)
+    for (int k = 0; k < 6; ++k) tb.m[t][k] = h_mats[t * 6 + k];
+  const int plane = m->cfg.n_frames * 17;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {
+    LaunchScope ls(m, SLOT_XFORM, n_items, s);
+    expand_transforms_kernel<<<grid_for(n_items * plane, kThreads, m->num_sms, 8), kThreads, 0, s>>>(d_base, d_out, tb, N, first_item, n_items, plane);
+  }
+  return check_launch("expand_transforms");
+}
+
 int mcd_window_loss(const mcd_model* m, const float* d_x0, const float* d_data, int64_t B, int32_t G, float* d_losses,
                     float* d_best, float* d_worst, void* stream) {
   MCD_TRY(check_ready(m));
@@ -1228,6 +1279,9 @@ int mcd_profile_slot_cost(const mcd_model* m, int slot, double* bytes_per_window
   } else if (slot == SLOT_BTLNK) {
     bytes = 4.0 * (m->cfg.cond_h_dim * m->Tc * 17 + m->E);
     flops = 2.0 * m->cfg.cond_h_dim * m->Tc * 17 * m->E;
+  } else if (slot == SLOT_XFORM) {
+    bytes = 4.0 * 2 * m->cfg.n_frames * 17 * 2;
+    flops = 6.0 * 2 * m->cfg.n_frames * 17;
   } else if (slot == SLOT_EMB) {
     bytes = 4.0 * (m->E + m->ws_emb);
     flops = 2.0 * m->E * m->ws_emb;

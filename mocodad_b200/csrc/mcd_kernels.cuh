@@ -605,6 +605,33 @@ __global__ void __launch_bounds__(kEmbThreads) time_embedding_kernel(const EmbTa
 }
 
 // ------------------------------------------------------------------------------------------
+// Dataset-item expansion: item idx of the reference's PoseDataset is the affine transform
+// idx / N of base window idx % N (utils/dataset.py:67-76, apply_pose_transform utils/dataset_utils.py:273-290:
+// einsum 'ktv,ck->ctv' over (x, y, 1)).  Base windows are uploaded once; the num_transform-fold dataset is
+// materialised on the device, tile by tile.  Products and sums are rounded separately, in the einsum's order.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxTransforms = 8;
+struct TransformTable {
+  float m[kMaxTransforms][6];  // rows 0 and 1 of the 3x3 matrix: x' = m0 x + m1 y + m2, y' = m3 x + m4 y + m5
+};
+__global__ void __launch_bounds__(kThreads) expand_transforms_kernel(const float* __restrict__ base, float* __restrict__ out,
+                                                                      const __grid_constant__ TransformTable tb, int64_t N,
+                                                                      int64_t first_item, int64_t n_items, int plane) {
+  const int64_t total = n_items * plane;  // plane = n_frames * V positions per coordinate channel
+  for (int64_t i = blockIdx.x * int64_t(kThreads) + threadIdx.x; i < total; i += int64_t(gridDim.x) * kThreads) {
+    const int64_t it = i / plane;
+    const int p = int(i - it * plane);
+    const int64_t idx = first_item + it;
+    const int64_t sample = idx % N;
+    const int tr = int(idx / N);
+    const float x = __ldg(base + (sample * 2) * plane + p), y = __ldg(base + (sample * 2 + 1) * plane + p);
+    const float* m = tb.m[tr];
+    out[(it * 2) * plane + p] = __fadd_rn(__fadd_rn(__fmul_rn(x, m[0]), __fmul_rn(y, m[1])), m[2]);
+    out[(it * 2 + 1) * plane + p] = __fadd_rn(__fadd_rn(__fmul_rn(x, m[3]), __fmul_rn(y, m[4])), m[5]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Bottleneck linear of the conditioning encoder: emb[n][l] = b[l] + sum_k h[n][k] * Wb[k][l]
 // h is planar-4 [n][C/4][P][4]; Wb was re-indexed at pack time to that order.  One warp / window.
 // ------------------------------------------------------------------------------------------

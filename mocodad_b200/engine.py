@@ -227,6 +227,37 @@ class ScoringEngine:
                                               int(first_window), out.data_ptr()))
         return out
 
+    # ------------------------------------------------------------------ f1: dataset items on the device
+    def expand_transforms(self, base: torch.Tensor, mats: np.ndarray, first_item: int, n_items: int) -> torch.Tensor:
+        """Dataset items ``first_item .. first_item + n_items - 1`` of the reference's ``PoseDataset`` built on the device:
+        item idx = transform ``idx // N`` (rows of ``mats`` [K,6]) of base window ``idx % N`` (utils/dataset.py:67-76)."""
+        N = base.shape[0]
+        self._chk(base, (N, N_COORDS, self.seg_len, N_JOINTS), "base")
+        mats = np.ascontiguousarray(mats, dtype=np.float32).reshape(-1, 6)
+        out = self._new(int(n_items), N_COORDS, self.seg_len, N_JOINTS)
+        with torch.cuda.device(self.device):
+            check(self.lib.mcd_expand_transforms(self._h, base.data_ptr(), N, mats.ctypes.data_as(_lib.c_float_p), mats.shape[0],
+                                                 int(first_item), int(n_items), out.data_ptr(), self._stream()))
+        return out
+
+    def score_dataset_host(self, base: torch.Tensor, n_generated_samples: int, *, num_transform: int = 5, batch: int = 1024,
+                           seed: int = 0) -> torch.Tensor:
+        """HOST in, HOST out over the whole ``num_transform``-fold dataset: the base windows [N,2,seg_len,V] cross PCIe
+        once, every batch of dataset items is expanded on the device (``expand_transforms``) and scored; Philox noise is
+        keyed by the dataset index, so the result equals scoring the materialised dataset batch by batch."""
+        if base.device.type != "cpu" or base.dtype != torch.float32 or not base.is_contiguous():
+            raise ValueError("score_dataset_host: need a contiguous float32 CPU tensor")
+        N = base.shape[0]
+        mats = pose_transform_matrices(num_transform)
+        d_base = base.to(self.device, non_blocking=True)
+        total = num_transform * N
+        scores = torch.empty(total, dtype=torch.float32, device=self.device)
+        for i0 in range(0, total, batch):
+            n = min(batch, total - i0)
+            items = self.expand_transforms(d_base, mats, i0, n)
+            scores[i0:i0 + n] = self.reverse_diffusion(items, n_generated_samples, seed=seed, first_window=i0)["best"]
+        return scores.cpu()
+
     # ------------------------------------------------------------------ host-side tables
     def schedule(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         return schedule(self.N)
@@ -252,6 +283,15 @@ class ScoringEngine:
                 "ms": ms[i], "launches": int(cnt[i]), "windows": int(win[i]),
                 "bytes_per_window": b.value, "flops_per_window": f.value}
         return res
+
+
+def pose_transform_matrices(num_transform: int = 5) -> np.ndarray:
+    """Rows 0-1 of the reference's ``ae_trans_list[:num_transform]`` (utils/dataset_utils.py:308-314) as [K,6] float32."""
+    lib = _lib.load()
+    out = np.empty((num_transform, 6), dtype=np.float32)
+    for k in range(num_transform):
+        check(lib.mcd_pose_transform_matrix(k, out[k].ctypes.data_as(_lib.c_float_p)))
+    return out
 
 
 def schedule(noise_steps: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:

@@ -110,3 +110,13 @@ def test_profile_slot_table(lib):
     names = [lib.mcd_profile_slot_name(i).decode() for i in range(n)]
     assert names[:11] == list(ref_port.UNET_BLOCKS)
     assert {"down1", "down2", "up3", "up2", "ddpm_step", "window_loss"} <= set(names)
+
+
+def test_pose_transform_matrices_match_reference(lib):
+    """ae_trans_list of the reference (utils/dataset_utils.py:255-270, 308-314), pinned by tests/golden/transforms.npz."""
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "transforms.npz"))["mats"]  # [5,3,3]
+    for k in range(5):
+        m = np.zeros(6, dtype=np.float32)
+        assert lib.mcd_pose_transform_matrix(k, m.ctypes.data_as(_lib.c_float_p)) == 0
+        assert np.array_equal(m.reshape(2, 3), gold[k, :2]), k
+    assert lib.mcd_pose_transform_matrix(5, m.ctypes.data_as(_lib.c_float_p)) != 0
