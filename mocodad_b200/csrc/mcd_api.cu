@@ -582,7 +582,7 @@ bool bn_fold(const mcd_model* m, const std::string& p, int C, std::vector<double
   return true;
 }
 
-struct BlockOffsets { size_t A, Tm, W, Wr, bias, WE, bE, Bop; bool has_bop; };
+struct BlockOffsets { size_t A, Tm, TmE, W, Wr, bias, WE, bE, Bop; bool has_bop; };
 
 bool pack_block(const mcd_model* m, Arena* ar, const std::string& p, int cin, int cout, int T, int V, bool emb, int E,
                 PackedBlock* pb, BlockOffsets* off, std::string* missing) {
@@ -617,6 +617,10 @@ bool pack_block(const mcd_model* m, Arena* ar, const std::string& p, int cin, in
   for (int v = 0; v < V; ++v)
     for (int t = 0; t < T; ++t)
       for (int q = 0; q < T; ++q) ar->h[off->Tm + size_t(v) * TMS + t * TP4 + q] = (*Tm)[(size_t(v) * T + t) * T + q];
+  off->TmE = ar->alloc(size_t(T) * T * V);
+  for (int v = 0; v < V; ++v)
+    for (int t = 0; t < T; ++t)
+      for (int q = 0; q < T; ++q) ar->h[off->TmE + (size_t(t) * T + q) * V + v] = (*Tm)[(size_t(v) * T + t) * T + q];
   off->W = ar->alloc(size_t(cinp) * cout);
   for (int k = 0; k < cin; ++k)
     for (int co = 0; co < cout; ++co) ar->h[off->W + size_t(k) * cout + co] = float(double((*W)[size_t(co) * cin + k]) * s[co]);
@@ -676,6 +680,7 @@ bool pack_block(const mcd_model* m, Arena* ar, const std::string& p, int cin, in
 void bind_block(PackedBlock* pb, const BlockOffsets& off, const float* base) {
   pb->w.A = base + off.A;
   pb->w.Tm = base + off.Tm;
+  pb->w.TmE = base + off.TmE;
   pb->w.Wt = base + off.W;
   pb->w.Wrt = pb->resconv ? base + off.Wr : nullptr;
   pb->w.bias = base + off.bias;

@@ -32,7 +32,7 @@ struct EdgeCfg {
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS) edge_block_kernel(const BlockWeights wt, const BlockIO io) {
   constexpr int T = Cfg::T, V = Cfg::V, P = Cfg::P, ROWS = Cfg::ROWS, NW = Cfg::NW;
-  constexpr int VP = Cfg::VP, TP4 = Cfg::TP4, TMS = Cfg::TMS, CW = Cfg::CW, CE = Cfg::CE;
+  constexpr int VP = Cfg::VP, CW = Cfg::CW, CE = Cfg::CE;
   constexpr bool HEAD = Cfg::HEAD;
   __shared__ float s0[2][ROWS];       // mix input  (2 channels)
   __shared__ float s1[2][ROWS];       // after the T-mix
@@ -107,11 +107,11 @@ __global__ void __launch_bounds__(Cfg::THREADS) edge_block_kernel(const BlockWei
     // T-mix: y1[c][q][v] = sum_t s0[c][t][v] * Tm[v][t][q]      (this thread: q = tq, v = vw)        stsgcn.py:154
     if (live) {
       float a0 = 0.f, a1 = 0.f;
-      const float* tp = wt.Tm + vw * TMS + tq;
+      const float* tp = wt.TmE + tq * V + vw;  // [t][q][v]: the lanes of a warp (consecutive joints) read one contiguous span
       const int base = wl * P + vw;
 #pragma unroll
       for (int t = 0; t < T; ++t) {
-        const float k = __ldg(tp + t * TP4);
+        const float k = __ldg(tp + t * T * V);
         a0 = fmaf(s0[0][base + t * V], k, a0);
         a1 = fmaf(s0[1][base + t * V], k, a1);
       }

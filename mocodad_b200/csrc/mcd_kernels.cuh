@@ -80,6 +80,7 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t window, u
 struct BlockWeights {
   const float* A;     // [T][V][VP]      gcn.A, rows zero-padded to VP = roundup4(V)
   const float* Tm;    // [V][TMS]        gcn.T as [v][t*TP4 + q], TMS = T*TP4 + 4
+  const float* TmE;   // [T][T][V]       gcn.T as [t][q][v] (edge blocks: a warp's lanes = consecutive joints read one span)
   const float* Wt;    // [CINP][COUT]    BN-folded tcn conv, transposed (k-major)
   const float* Wrt;   // [CINP][COUT]    BN-folded residual conv (nullptr: identity residual)
   const float* bias;  // [COUT]          folded biases (tcn + residual)
