@@ -263,10 +263,17 @@ struct TcCfg {
   static constexpr int TA = CS_A * TAR;
   static constexpr int WS_A = (kTcMix / TA) < NW ? (kTcMix / TA) : NW;
   static_assert(TT <= kTcMix && TA <= kTcMix && WS_T >= 1 && WS_A >= 1, "mix task mapping");
-  static constexpr int ACC_COLS = MT * COUT;  // one accumulator set; TMEM holds two (tile parity)
+  // "N-merge" (blocks with a residual convolution whose accumulators fit twice): the hi and lo weight parts sit back to back
+  // in the operand array, so ONE MMA with N = 2*COUT forms act_hi*W_hi (columns [0,COUT)) and act_hi*W_lo (columns
+  // [COUT,2*COUT)) from a single read of the activation operand; a second MMA adds act_lo*W_hi.  Two MMAs and 14 KB of
+  // operand reads per product instead of three and 18 KB (COUT=64) -- the V=10 blocks are bound by exactly that traffic.
+  // The epilogue adds the two column halves.
+  static constexpr bool NMERGE = RESCONV && 2 * MT * 2 * COUT <= 512 && 2 * COUT <= 256;
+  static constexpr int TCOLS = NMERGE ? 2 * COUT : COUT;  // accumulator columns per 128-row tile
+  static constexpr int ACC_COLS = MT * TCOLS;  // one accumulator set; TMEM holds two (tile parity)
   static constexpr int TMEM_COLS = 2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512);
   static_assert(CIN % KC == 0 && COUT % 32 == 0 && COUT <= 256, "tensor-core block: Cin multiple of 16, Cout multiple of 32");
-  static_assert(2 * MT * COUT <= 512, "two accumulator sets exceed TMEM");
+  static_assert(2 * ACC_COLS <= 512, "two accumulator sets exceed TMEM");
   static_assert(ROWS % 8 == 0, "operand arrays must be whole swizzle atoms");
   // shared memory carve-up, in floats from a 1024-byte aligned base
   static constexpr int ARR = ROWS * 16;          // one operand array [ROWS][16] (a multiple of 512 bytes)
@@ -584,7 +591,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
     reg_dec<kRegsS>();
     if (warp == kTcMmaWarp) {
     // =============================== MMA-issuing warp ===============================
-    const uint32_t idesc = umma_idesc_tf32(COUT);
+    const uint32_t idesc = umma_idesc_tf32(COUT), idesc2 = umma_idesc_tf32(2 * COUT);
+    constexpr bool NMERGE = Cfg::NMERGE;
+    constexpr int TCOLS = Cfg::TCOLS;
     // operand descriptors of every buffer, computed once (warp-uniform): inside the loop a descriptor is base + constant
     const uint64_t dY2_0 = umma_desc_sw64(smem_u32(sY2)), dY2lo_0 = umma_desc_sw64(smem_u32(sY2lo));
     const uint64_t dW_0 = umma_desc_sw64(smem_u32(sWc)), dW_1 = umma_desc_sw64(smem_u32(sWc + WCH));
@@ -607,13 +616,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       if (elect_one()) {
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
-          const uint32_t d = d0 + m * COUT;
+          const uint32_t d = d0 + m * TCOLS;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {  // two K=8 steps per 16-channel chunk: c4 planes (2h, 2h+1)
             const uint64_t ao = uint64_t((m * 128 * 16 + h * 2 * ROWS * 16) >> 4), bo = uint64_t((h * 32) >> 4);
-            umma_tf32(d, xLo + ao, bW + 2 * PART + bo, idesc, (cj > 0 || h > 0) ? 1u : 0u);
-            umma_tf32(d, xHi + ao, bW + 3 * PART + bo, idesc, 1u);
-            umma_tf32(d, xHi + ao, bW + 2 * PART + bo, idesc, 1u);
+            const uint32_t first = (cj > 0 || h > 0) ? 1u : 0u;  // the very first MMA of a tile clears its accumulator columns
+            if constexpr (NMERGE) {
+              umma_tf32(d, xHi + ao, bW + 2 * PART + bo, idesc2, first);  // X_hi * [Wr_hi | Wr_lo]
+              umma_tf32(d, xLo + ao, bW + 2 * PART + bo, idesc, 1u);      // X_lo * Wr_hi
+            } else {
+              umma_tf32(d, xLo + ao, bW + 2 * PART + bo, idesc, first);
+              umma_tf32(d, xHi + ao, bW + 3 * PART + bo, idesc, 1u);
+              umma_tf32(d, xHi + ao, bW + 2 * PART + bo, idesc, 1u);
+            }
           }
         }
         umma_commit(BAR(BAR_RES_DONE + s));  // Xlo buffer free again
@@ -648,13 +663,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       if (elect_one()) {
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
-          const uint32_t d = d0 + m * COUT;
+          const uint32_t d = d0 + m * TCOLS;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {  // two K=8 steps per 64-byte operand row
             const uint64_t ao = uint64_t((m * 128 * 64 + h * 32) >> 4), bo = uint64_t((h * 32) >> 4);
-            umma_tf32(d, aLo + ao, bW + bo, idesc, h == 0 ? acc0 : 1u);
-            umma_tf32(d, aHi + ao, bW + PART + bo, idesc, 1u);
-            umma_tf32(d, aHi + ao, bW + bo, idesc, 1u);
+            if constexpr (NMERGE) {
+              umma_tf32(d, aHi + ao, bW + bo, idesc2, 1u);  // Y2_hi * [W_hi | W_lo]   (the residual MMAs cleared the tile)
+              umma_tf32(d, aLo + ao, bW + bo, idesc, 1u);   // Y2_lo * W_hi
+            } else {
+              umma_tf32(d, aLo + ao, bW + bo, idesc, h == 0 ? acc0 : 1u);
+              umma_tf32(d, aHi + ao, bW + PART + bo, idesc, 1u);
+              umma_tf32(d, aHi + ao, bW + bo, idesc, 1u);
+            }
           }
         }
         umma_commit(BAR(BAR_MMA_DONE + s));
@@ -786,13 +806,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
           }
           uint32_t acc[32];
           const long long t_ld = MCD_CLOCK();
-          tmem_ld32(tmem + (uint32_t(q * 32) << 16) + uint32_t(set * Cfg::ACC_COLS + m * COUT + c0), acc);
+          const uint32_t tcol = tmem + (uint32_t(q * 32) << 16) + uint32_t(set * Cfg::ACC_COLS + m * Cfg::TCOLS + c0);
+          tmem_ld32(tcol, acc);
+          uint32_t acc2[Cfg::NMERGE ? 32 : 1];
+          if constexpr (Cfg::NMERGE) tmem_ld32(tcol + COUT, acc2);  // the act_hi * W_lo partial sums
           // bias / embedding of the first two 4-channel groups travel while the TMEM load is in flight; the rest is
           // fetched two groups ahead (shared-memory latency is ~100 cycles with the mixes and the tensor pipe on the port)
           const float4* bp = reinterpret_cast<const float4*>(sBias + c0);
           const float4* ep = reinterpret_cast<const float4*>(embp + c0);
           float4 b4[2] = {bp[0], bp[1]}, e4[2] = {ep[0], ep[1]};
           tmem_ld_wait(acc);
+          if constexpr (Cfg::NMERGE) {
+            tmem_ld_wait(acc2);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(acc2[i]));
+          }
           PHASE(2, t_ld);
           const long long t_st = MCD_CLOCK();
 #pragma unroll
