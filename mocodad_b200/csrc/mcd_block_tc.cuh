@@ -40,6 +40,15 @@
 #ifndef MCD_EXP_SKIP_A
 #define MCD_EXP_SKIP_A 0  // experiment only (wrong results): the A-mix warps skip their arithmetic
 #endif
+#ifndef MCD_EXP_SKIP_EPI
+#define MCD_EXP_SKIP_EPI 0  // experiment only: the epilogue warps skip TMEM loads, arithmetic and stores
+#endif
+#ifndef MCD_EXP_EPI_NOMEM
+#define MCD_EXP_EPI_NOMEM 0  // experiment only: the epilogue does its arithmetic but no global loads / stores
+#endif
+#ifndef MCD_EXP_SKIP_MMA
+#define MCD_EXP_SKIP_MMA 0  // experiment only: the MMA warp issues no MMAs (commits still arrive)
+#endif
 
 namespace mcd {
 
@@ -615,7 +624,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       const uint64_t xHi = dX_0 + uint64_t(b) * ARR16, xLo = dXlo_0 + uint64_t(j % (Cfg::NXLO > 0 ? Cfg::NXLO : 1)) * ARR16;
       if (elect_one()) {
 #pragma unroll
-        for (int m = 0; m < MT; ++m) {
+        for (int m = 0; m < (MCD_EXP_SKIP_MMA ? 0 : MT); ++m) {
           const uint32_t d = d0 + m * TCOLS;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {  // two K=8 steps per 16-channel chunk: c4 planes (2h, 2h+1)
@@ -662,7 +671,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       const uint32_t acc0 = (RESCONV || chunk > 0) ? 1u : 0u;
       if (elect_one()) {
 #pragma unroll
-        for (int m = 0; m < MT; ++m) {
+        for (int m = 0; m < (MCD_EXP_SKIP_MMA ? 0 : MT); ++m) {
           const uint32_t d = d0 + m * TCOLS;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {  // two K=8 steps per 64-byte operand row
@@ -788,7 +797,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       if (warp == kTcEpiWarp0) TRACE(4, ti, 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int m = 0; m < MT; ++m) {
+      for (int m = 0; m < (MCD_EXP_SKIP_EPI ? 0 : MT); ++m) {
         const int r = m * 128 + q * 32 + lane;
         const int wl = r / P;
         const int64_t w = tile * NW + wl;
@@ -802,7 +811,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
           float* op = io.out + (ok ? act_off(w, c0 >> 2, pp, COUT, P) : 0);
           if constexpr (!RESCONV) {  // identity residual: issue the loads of this column group before touching TMEM
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) xr[j4] = ldg_nc4(ip + j4 * P * 4);  // 4-channel planes are P elements apart
+            for (int j4 = 0; j4 < 8; ++j4) xr[j4] = MCD_EXP_EPI_NOMEM ? make_float4(0.f, 0.f, 0.f, float(j4)) : ldg_nc4(ip + j4 * P * 4);  // 4-channel planes are P elements apart
           }
           uint32_t acc[32];
           const long long t_ld = MCD_CLOCK();
@@ -835,7 +844,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
               v = v > 0.f ? v : slope * v;
               o[jj] = v + f4get(ec, jj);
             }
-            stg4_pred(op + j4 * P * 4, make_float4(o[0], o[1], o[2], o[3]), ok);
+            stg4_pred(op + j4 * P * 4, make_float4(o[0], o[1], o[2], o[3]), ok && !(MCD_EXP_EPI_NOMEM && o[0] != 12345.f));
           }
           PHASE(3, t_st);
         }

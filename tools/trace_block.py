@@ -4,7 +4,7 @@ usage (on the GPU box): python tools/trace_block.py [slot=2] [n_windows=2368] [e
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["MOCODAD_B200_LIB"] = os.path.join(ROOT, "mocodad_b200", "libmocodad_b200_trace.so")
+os.environ.setdefault("MOCODAD_B200_LIB", os.path.join(ROOT, "mocodad_b200", "libmocodad_b200_trace.so"))
 import torch
 from mocodad_b200 import ScoringEngine, synthetic as synth
 from mocodad_b200._lib import check
