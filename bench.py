@@ -297,7 +297,8 @@ def run_b200(a):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
     if os.path.exists(tpath):
-        per_window = json.load(open(tpath))["dram_bytes_per_window"].get(top["kernel"])
+        tj = json.load(open(tpath))
+        per_window = tj["dram_bytes_per_window"].get(top["kernel"]) if tj.get("T", 24) == T else None  # captured at T=24
         if per_window is not None:
             traffic = per_window * pv["windows"] / pv["launches"]
     # tensor-pipe view of the same kernel: 3xTF32 executes 3 tf32 MMAs per fp32 product of the 1x1 convolution(s)
