@@ -391,7 +391,9 @@ size_t carve_bytes(const mcd_model* m, int64_t n) {
 
 // ---- the denoiser ----------------------------------------------------------------------------
 int unet_forward_impl(const mcd_model* m, const float* d_x, int64_t n, int t, const float* d_cond, int64_t condB,
-                      int64_t w0, float* d_eps, const Workspace& ws, cudaStream_t s, const char* tap, float* tap_out) {
+                      int64_t w0, float* d_eps, const Workspace& ws, cudaStream_t s, const char* tap, float* tap_out,
+                      const DdpmArgs* fuse_ddpm = nullptr) {
+  // fuse_ddpm: the last block applies the DDPM update and writes x_{t-1} over d_x in place (d_eps is not produced)
   if (t < 0 || t >= m->N) return fail(MCD_ERR_INVALID_ARG, "step t=%d outside [0,%d)", t, m->N);
   const int T = m->T;
   BlockIO io{};
@@ -420,6 +422,11 @@ int unet_forward_impl(const mcd_model* m, const float* d_x, int64_t n, int t, co
     if (idx == kNumUnetBlocks - 1) {
       io.xres = (tap != nullptr && strcmp(tap, kUnetBlocks[idx].name) == 0) ? nullptr : d_x;
       if (io.xres == nullptr) io.out = tap_out;  // the layer's own output, reference layout
+      if (fuse_ddpm != nullptr && io.xres != nullptr) {
+        io.fuse_ddpm = 1;
+        io.ddpm = *fuse_ddpm;
+        io.out = const_cast<float*>(d_x);
+      }
     }
     MCD_TRY(unet_block_dispatch(1, T, idx, m, &m->unet[idx].w, &io, s));
     if (idx != kNumUnetBlocks - 1) MCD_TRY(tap_copy(kUnetBlocks[idx].name, out, kUnetBlocks[idx].cout, kPyramid[kUnetBlocks[idx].level]));
@@ -1149,9 +1156,9 @@ int mcd_reverse_diffusion(const mcd_model* m, const float* d_data, int64_t B, in
     MCD_TRY(launch_randn(m, x, n, make_ddpm_args(m, 0, d_noise, B, 0, v0, seed, first_window), s));
     int slot = 0;
     for (int t = m->N - 1; t >= 1; --t) {  // mocodad.py:163
-      MCD_TRY(unet_forward_impl(m, x, n, t, cond_emb, B, v0, ws.eps, ws, s, nullptr, nullptr));
-      ++slot;
-      MCD_TRY(launch_ddpm(m, x, ws.eps, n, make_ddpm_args(m, t, d_noise, B, slot, v0, seed, first_window), s));
+      ++slot;  // mocodad.py:172-178: the DDPM update runs inside the last block of the denoiser
+      const DdpmArgs dd = make_ddpm_args(m, t, d_noise, B, slot, v0, seed, first_window);
+      MCD_TRY(unet_forward_impl(m, x, n, t, cond_emb, B, v0, ws.eps, ws, s, nullptr, nullptr, &dd));
     }
     MCD_TRY(launch_loss(m, x, d_data, losses + v0, n, v0, B, s));  // mocodad.py:484
   }

@@ -154,7 +154,25 @@ __global__ void __launch_bounds__(Cfg::THREADS) edge_block_kernel(const BlockWei
           v0 = (v0 > 0.f ? v0 : slope * v0) + sEmb[wl][0];
           v1 = (v1 > 0.f ? v1 : slope * v1) + sEmb[wl][1];
           const int64_t e0 = (w * 2) * P + p;
-          if (io.xres != nullptr) { v0 += __ldg(io.xres + e0); v1 += __ldg(io.xres + e0 + P); }
+          float x0v = 0.f, x1v = 0.f;
+          if (io.xres != nullptr) { x0v = __ldg(io.xres + e0); x1v = __ldg(io.xres + e0 + P); v0 += x0v; v1 += x1v; }
+          if (io.fuse_ddpm) {  // mocodad.py:172-178 on (x, eps = v) of this thread's two elements; same roundings as ddpm_step_kernel
+            const DdpmArgs& a = io.ddpm;
+            float z0 = 0.f, z1 = 0.f;
+            if (a.add_noise) {
+              const int64_t virt = a.virt0 + w;
+              const int64_t g = virt / a.noise_B, b = virt - g * a.noise_B;
+              if (a.noise != nullptr) {
+                const float* np = a.noise + ((g * a.noise_slots + a.slot) * a.noise_B + b) * (2 * P);
+                z0 = np[p]; z1 = np[P + p];
+              } else {
+                z0 = philox_normal(a.seed, uint64_t(a.first_window + b), uint32_t(g), uint32_t(a.slot), uint32_t(p));
+                z1 = philox_normal(a.seed, uint64_t(a.first_window + b), uint32_t(g), uint32_t(a.slot), uint32_t(P + p));
+              }
+            }
+            v0 = __fadd_rn(__fmul_rn(a.c1, __fsub_rn(x0v, __fmul_rn(a.c2, v0))), __fmul_rn(a.c3, z0));
+            v1 = __fadd_rn(__fmul_rn(a.c1, __fsub_rn(x1v, __fmul_rn(a.c2, v1))), __fmul_rn(a.c3, z1));
+          }
           io.out[e0] = v0;
           io.out[e0 + P] = v1;
         }

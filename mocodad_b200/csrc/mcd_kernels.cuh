@@ -91,6 +91,20 @@ struct BlockWeights {
   float prelu;        // prelu.weight[0]
 };
 
+// DDPM update x <- c1 (x - c2 eps) + c3 z (models/mocodad.py:172-178): arguments of ddpm_step_kernel, and of the last denoiser
+// block when the update is fused into it
+struct DdpmArgs {
+  float c1, c2, c3;       // 1/sqrt(alpha_t), (1-alpha_t)/sqrt(1-alpha_hat_t), sqrt(beta_t)
+  int add_noise;          // 0 at t == 1
+  const float* noise;     // nullptr => Philox
+  int64_t noise_B;        // windows per sample B: virtual index = g*B + b (always set)
+  int32_t noise_slots;    // N-1
+  int32_t slot;           // which slot this step reads / Philox slot id
+  int64_t virt0;          // virtual index of window 0 of this call (for noise addressing)
+  uint64_t seed;
+  int64_t first_window;   // global (dataset) id of window b = 0 (Philox counter base)
+};
+
 struct BlockIO {
   const float* in;    // channel-last [n][P][CIN]  (IN_CL)  or channel-first source (IN_CF)
   float* out;         // channel-last [n][P][COUT] (OUT_CL) or [n][2][P] eps      (OUT_EPS)
@@ -109,6 +123,10 @@ struct BlockIO {
   // this block's COUT values at column emb_off
   const float* emb;
   int32_t emb_stride, emb_off;
+  // last denoiser block only: apply the DDPM update to its eps and write x_{t-1} to `out` (= the x buffer, in place: every
+  // element is read and written by the same thread) instead of eps; saves the round trip of eps through HBM and a launch
+  int32_t fuse_ddpm;
+  DdpmArgs ddpm;
 };
 
 enum { IN_CL = 0, IN_CF = 1 };
@@ -671,18 +689,6 @@ __global__ void __launch_bounds__(kThreads) bottleneck_kernel(const float* __res
 //   noise: pre-drawn tensor addressed as noise[(g*slots + slot)*B + b][2P] for virtual window
 //   w = g*B + b (pass B = n, g = 0 for a plain [n,2P] tensor), or nullptr => Philox.
 // ------------------------------------------------------------------------------------------
-struct DdpmArgs {
-  float c1, c2, c3;       // 1/sqrt(alpha_t), (1-alpha_t)/sqrt(1-alpha_hat_t), sqrt(beta_t)
-  int add_noise;          // 0 at t == 1
-  const float* noise;     // nullptr => Philox
-  int64_t noise_B;        // windows per sample B: virtual index = g*B + b (always set)
-  int32_t noise_slots;    // N-1
-  int32_t slot;           // which slot this step reads / Philox slot id
-  int64_t virt0;          // virtual index of window 0 of this call (for noise addressing)
-  uint64_t seed;
-  int64_t first_window;   // global (dataset) id of window b = 0 (Philox counter base)
-};
-
 __global__ void __launch_bounds__(kThreads) ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ eps,
                                                              int64_t n, int per_window, DdpmArgs a) {
   const int64_t total = n * per_window;

@@ -300,8 +300,8 @@ def test_launch_counter_and_profile_slots():
     prof = eng.profile_read()
     eng.profile_enable(False)
     launched = eng.launch_count() - n0
-    # encoder 4+1, per tile: randn + 3 steps x (time embedding + 15 + ddpm) + loss, + best
-    assert launched == 5 + 1 + 3 * 17 + 1 + 1
+    # encoder 4+1, per tile: randn + 3 steps x (time embedding + 15; the DDPM update is fused into the last block) + loss, + best
+    assert launched == 5 + 1 + 3 * 16 + 1 + 1
     assert sum(v["launches"] for v in prof.values()) == launched
     assert prof["st_gcnnsd3.0"]["launches"] == 3 and prof["st_gcnnsd3.0"]["windows"] == 3 * 32
     assert all(v["ms"] > 0 for v in prof.values() if v["launches"])
