@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 2
+#define MCD_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define MCD_API __attribute__((visibility("default")))
@@ -147,6 +147,25 @@ MCD_API int mcd_randn_windows(const mcd_model* m, float* d_x, int64_t n, uint64_
 MCD_API int mcd_pose_transform_matrix(int32_t index, float* h_mat6);
 MCD_API int mcd_expand_transforms(const mcd_model* m, const float* d_base, int64_t N, const float* h_mats,
                           int32_t num_transform, int64_t first_item, int64_t n_items, float* d_out, void* stream);
+
+/* ---- f1, second slice: trajectory frame rows -> dataset items, without a host-side window tensor ----------
+ * mcd_normalize_frames: Trajectory._from_image_to_centre_bounding_box (utils/data.py:165-187) over
+ * compute_bounding_box (utils/data.py:11-44) for F frame rows [F,34] = (x1,y1,...,x17,y17) in image
+ * coordinates; (0,0) marks a missing joint.  d_out [F,34] may alias d_rows.  Bit-identical to the
+ * reference's float32 numpy arithmetic (numpy >= 2 promotion rules, as pinned by the oracle).
+ * mcd_build_items: dataset item idx = first_item + i is transform idx / N of window idx % N
+ * (utils/dataset.py:67-76); window w is rows d_win_start[w] + k * row_step, k < n_frames, of the
+ * normalised frame array (utils/preprocessing.py:55-86), scaled by the fitted RobustScaler
+ * (utils/data.py:345-354: zeros are missing and stay zero; h_center / h_scale [34] = center_ / scale_)
+ * and laid out [2,n_frames,17] (utils/dataset.py:241-256).  h_mats [num_transform][6] as for
+ * mcd_expand_transforms (NULL = the identity, num_transform must be 1: the base windows).
+ * d_win_start [N] int64 on the device; the caller guarantees every window lies inside [0,F).
+ * d_out [n_items,2,n_frames,17]. */
+MCD_API int mcd_normalize_frames(const mcd_model* m, const float* d_rows, int64_t F, float vid_w, float vid_h,
+                         float* d_out, void* stream);
+MCD_API int mcd_build_items(const mcd_model* m, const float* d_rows, int64_t F, const int64_t* d_win_start, int64_t N,
+                    int32_t row_step, const double* h_center, const double* h_scale, const float* h_mats,
+                    int32_t num_transform, int64_t first_item, int64_t n_items, float* d_out, void* stream);
 
 /* ---- a11: per-window loss + aggregation, mocodad.py:454-520 --------------------------------
  * d_x0 [G*B,2,T,V] sample-major; d_data [B,2,n_frames,V] (the corrupt frames are the target).

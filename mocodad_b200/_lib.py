@@ -13,6 +13,7 @@ from typing import Optional
 from . import _build
 
 c_float_p = C.POINTER(C.c_float)
+c_double_p = C.POINTER(C.c_double)
 
 
 class McdConfig(C.Structure):
@@ -56,6 +57,9 @@ SIGNATURES = {
     "mcd_pose_transform_matrix": (C.c_int, [C.c_int32, c_float_p]),
     "mcd_expand_transforms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_float_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p,
                                         C.c_void_p]),
+    "mcd_normalize_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "mcd_build_items": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, c_double_p, c_double_p,
+                                  c_float_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "mcd_window_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
     "mcd_reverse_diffusion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_uint64,
@@ -103,8 +107,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.mcd_abi_version() != 2:
-        raise ImportError(f"{path}: ABI version {lib.mcd_abi_version()} != 2 (stale build?)")
+    if lib.mcd_abi_version() != 3:
+        raise ImportError(f"{path}: ABI version {lib.mcd_abi_version()} != 3 (stale build?)")
     _LIB = lib
     return lib
 

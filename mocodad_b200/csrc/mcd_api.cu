@@ -72,6 +72,8 @@ enum Slot {
   SLOT_TAP,
   SLOT_EMB,                             // time / condition embedding of all tensor-core blocks (one launch per denoiser call)
   SLOT_XFORM,                           // dataset-item expansion (affine transforms of the base windows)
+  SLOT_NORM,                            // window ingest: bounding-box-centre coordinates per frame row (unit: frame rows)
+  SLOT_ITEMS,                           // window ingest: frame rows -> robust-scaled, transformed dataset items
   SLOT_COUNT
 };
 const char* kSlotNames[SLOT_COUNT] = {
@@ -79,7 +81,7 @@ const char* kSlotNames[SLOT_COUNT] = {
     "st_gcnnsd3.1",  "st_gcnnsu4.0", "st_gcnnsu4.1", "st_gcnnsu3.0", "st_gcnnsu3.1", "down1",
     "down2",         "up3",          "up2",          "ddpm_step",    "randn",        "window_loss",
     "best_worst",    "cond.enc0",    "cond.enc1",    "cond.enc2",    "cond.enc3",    "cond.btlnk",
-    "tap_transpose", "time_embedding", "expand_transforms"};
+    "tap_transpose", "time_embedding", "expand_transforms", "normalize_frames", "build_items"};
 
 constexpr int nw_for(int T, int V0) {  // windows per CTA tile: ~408 (frame,joint) rows at the widest level
   return (408 / (T * V0)) > 0 ? 408 / (T * V0) : 1;
@@ -1086,6 +1088,58 @@ int mcd_expand_transforms(const mcd_model* m, const float* d_base, int64_t N, co
   return check_launch("expand_transforms");
 }
 
+int mcd_normalize_frames(const mcd_model* m, const float* d_rows, int64_t F, float vid_w, float vid_h, float* d_out, void* stream) {
+  MCD_TRY(check_ready(m));
+  if (d_rows == nullptr || d_out == nullptr || F < 0) return fail(MCD_ERR_INVALID_ARG, "mcd_normalize_frames: bad argument");
+  if (!(vid_w >= 1.f) || !(vid_h >= 1.f)) return fail(MCD_ERR_INVALID_ARG, "mcd_normalize_frames: video resolution %g x %g", vid_w, vid_h);
+  if ((reinterpret_cast<uintptr_t>(d_rows) | reinterpret_cast<uintptr_t>(d_out)) & 7)
+    return fail(MCD_ERR_INVALID_ARG, "mcd_normalize_frames: frame rows must be 8-byte aligned");
+  if (F == 0) return MCD_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {
+    LaunchScope ls(m, SLOT_NORM, F, s);
+    normalize_frames_kernel<<<grid_for(F * 32, kThreads, m->num_sms, 8), kThreads, 0, s>>>(d_rows, d_out, F, vid_w, vid_h);
+  }
+  return check_launch("normalize_frames");
+}
+
+int mcd_build_items(const mcd_model* m, const float* d_rows, int64_t F, const int64_t* d_win_start, int64_t N, int32_t row_step,
+                    const double* h_center, const double* h_scale, const float* h_mats, int32_t num_transform, int64_t first_item,
+                    int64_t n_items, float* d_out, void* stream) {
+  MCD_TRY(check_ready(m));
+  if (d_rows == nullptr || d_win_start == nullptr || d_out == nullptr || h_center == nullptr || h_scale == nullptr || F < 1 || N < 1 ||
+      n_items < 0 || first_item < 0 || row_step < 1)
+    return fail(MCD_ERR_INVALID_ARG, "mcd_build_items: bad argument");
+  if (reinterpret_cast<uintptr_t>(d_rows) & 7) return fail(MCD_ERR_INVALID_ARG, "mcd_build_items: frame rows must be 8-byte aligned");
+  if (h_mats == nullptr && num_transform != 1) return fail(MCD_ERR_INVALID_ARG, "mcd_build_items: h_mats may be NULL only with one (identity) transform");
+  if (num_transform < 1 || num_transform > kMaxTransforms)
+    return fail(MCD_ERR_UNSUPPORTED, "mcd_build_items: %d transforms (1..%d supported)", num_transform, kMaxTransforms);
+  if (first_item + n_items > int64_t(num_transform) * N)
+    return fail(MCD_ERR_INVALID_ARG, "mcd_build_items: items [%lld, %lld) exceed the dataset of %d x %lld items", (long long)first_item,
+                (long long)(first_item + n_items), num_transform, (long long)N);
+  if (int64_t(m->cfg.n_frames - 1) * row_step + 1 > F)
+    return fail(MCD_ERR_INVALID_ARG, "mcd_build_items: %lld frame rows cannot hold one window of %d rows, step %d", (long long)F,
+                m->cfg.n_frames, row_step);
+  if (n_items == 0) return MCD_OK;
+  ScalerTable sc{};
+  for (int k = 0; k < 34; ++k) {
+    if (!(h_scale[k] != 0.0)) return fail(MCD_ERR_INVALID_ARG, "mcd_build_items: scale[%d] is zero or NaN", k);
+    sc.center[k] = h_center[k];
+    sc.scale[k] = h_scale[k];
+  }
+  TransformTable tb{};
+  const float ident[6] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f};
+  for (int t = 0; t < num_transform; ++t)
+    for (int k = 0; k < 6; ++k) tb.m[t][k] = h_mats ? h_mats[t * 6 + k] : ident[k];
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {
+    LaunchScope ls(m, SLOT_ITEMS, n_items, s);
+    build_items_kernel<<<grid_for(n_items * m->cfg.n_frames * 17, kThreads, m->num_sms, 8), kThreads, 0, s>>>(
+        d_rows, d_win_start, sc, tb, N, first_item, n_items, m->cfg.n_frames, row_step, d_out);
+  }
+  return check_launch("build_items");
+}
+
 int mcd_window_loss(const mcd_model* m, const float* d_x0, const float* d_data, int64_t B, int32_t G, float* d_losses,
                     float* d_best, float* d_worst, void* stream) {
   MCD_TRY(check_ready(m));
@@ -1294,6 +1348,12 @@ int mcd_profile_slot_cost(const mcd_model* m, int slot, double* bytes_per_window
   } else if (slot == SLOT_XFORM) {
     bytes = 4.0 * 2 * m->cfg.n_frames * 17 * 2;
     flops = 6.0 * 2 * m->cfg.n_frames * 17;
+  } else if (slot == SLOT_NORM) {  // per frame row: read + write 34 floats
+    bytes = 4.0 * 34 * 2;
+    flops = 2.0 * 34 + 20;
+  } else if (slot == SLOT_ITEMS) {  // per item: n_frames rows read (L2-shared between items), [2, n_frames, 17] written
+    bytes = 4.0 * 2 * m->cfg.n_frames * 17 * 2;
+    flops = 10.0 * 2 * m->cfg.n_frames * 17;
   } else if (slot == SLOT_EMB) {
     bytes = 4.0 * (m->E + m->ws_emb);
     flops = 2.0 * m->E * m->ws_emb;

@@ -651,6 +651,91 @@ __global__ void __launch_bounds__(kThreads) expand_transforms_kernel(const float
 }
 
 // ------------------------------------------------------------------------------------------
+// Window ingest (second slice): raw trajectory rows -> dataset items, on the device.
+//
+// normalize_frames_kernel: Trajectory._from_image_to_centre_bounding_box (utils/data.py:165-187) with
+// compute_bounding_box (utils/data.py:11-44) for every frame row [34] = (x1, y1, ..., x17, y17).  One warp per frame:
+// lane v < 17 owns joint v (one coalesced 8-byte load per lane), the box is four warp-shuffle min / max reductions over the
+// non-zero coordinates.  The reference computes in float32 with every operation rounded separately (numpy scalars,
+// Python ints for the rounded corners), so every step below is an explicit _rn intrinsic -- no FMA contraction.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float clip_round(float v, float hi) {  // int(round(np.clip(v, 0, hi))): half to even
+  return rintf(fminf(fmaxf(v, 0.f), hi));
+}
+__global__ void __launch_bounds__(kThreads) normalize_frames_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t F,
+                                                                    float vid_w, float vid_h) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t(gridDim.x) * kThreads) >> 5;
+  const float inf = __int_as_float(0x7f800000);
+  const float wl = __fsub_rn(vid_w, 1.f), hl = __fsub_rn(vid_h, 1.f);
+  for (int64_t f = (blockIdx.x * int64_t(kThreads) + threadIdx.x) >> 5; f < F; f += warps) {
+    float2 kp = make_float2(0.f, 0.f);
+    if (lane < 17) kp = *reinterpret_cast<const float2*>(in + f * 34 + 2 * lane);
+    const bool hx = kp.x != 0.f, hy = kp.y != 0.f;   // zeros are missing coordinates (data.py:27)
+    const float left = warp_min(hx ? kp.x : inf), right = warp_max(hx ? kp.x : -inf);
+    const float top = warp_min(hy ? kp.y : inf), bottom = warp_max(hy ? kp.y : -inf);
+    float ox = 0.f, oy = 0.f;
+    // no non-zero x or no non-zero y: np.min raises -> box (0,0,0,0) -> zero width and height -> zeros (data.py:28-32, 182-183)
+    if (left <= right && top <= bottom) {
+      const float ew = __fmul_rn(0.1f, __fadd_rn(__fsub_rn(right, left), 1.f));   // data.py:34
+      const float eh = __fmul_rn(0.1f, __fadd_rn(__fsub_rn(bottom, top), 1.f));
+      const float L = clip_round(__fsub_rn(left, ew), wl), R = clip_round(__fadd_rn(right, ew), wl);   // data.py:35-41
+      const float T = clip_round(__fsub_rn(top, eh), hl), B = clip_round(__fadd_rn(bottom, eh), hl);
+      const float cx = __fmul_rn(__fadd_rn(L, R), 0.5f), cy = __fmul_rn(__fadd_rn(T, B), 0.5f);     // exact: small integers
+      const float bw = __fsub_rn(R, L), bh = __fsub_rn(B, T);
+      if (bw != 0.f) ox = __fdiv_rn(__fsub_rn(hx ? kp.x : cx, cx), bw);            // data.py:178-182
+      if (bh != 0.f) oy = __fdiv_rn(__fsub_rn(hy ? kp.y : cy, cy), bh);
+    }
+    if (lane < 17) *reinterpret_cast<float2*>(out + f * 34 + 2 * lane) = make_float2(ox, oy);
+  }
+}
+
+// build_items_kernel: dataset item idx = first_item + i is transform idx / N of window idx % N (utils/dataset.py:67-76), the
+// window being rows start, start + step, ... of the normalised frame array (utils/preprocessing.py:55-86), robust-scaled
+// (utils/data.py:345-354: 0 -> missing -> 0; sklearn's `X -= center_; X /= scale_` on float32 rows, each a double operation
+// rounded to float32, which equals the float32 operation when the attribute is float32), laid out [2, L, 17]
+// (utils/dataset.py:241-256) and transformed like expand_transforms_kernel.  No window tensor is ever materialised: a frame row
+// is read from L2 by the up to L x num_transform items that share it.
+struct ScalerTable {
+  double center[34], scale[34];
+};
+__global__ void __launch_bounds__(kThreads) build_items_kernel(const float* __restrict__ rows, const int64_t* __restrict__ win_start,
+                                                               const __grid_constant__ ScalerTable sc,
+                                                               const __grid_constant__ TransformTable tb, int64_t N, int64_t first_item,
+                                                               int64_t n_items, int seg_len, int row_step, float* __restrict__ out) {
+  const int plane = seg_len * 17;
+  const int64_t total = n_items * plane;
+  for (int64_t i = blockIdx.x * int64_t(kThreads) + threadIdx.x; i < total; i += int64_t(gridDim.x) * kThreads) {
+    const int64_t it = i / plane;
+    const int p = int(i - it * plane);
+    const int t = p / 17, v = p - t * 17;
+    const int64_t idx = first_item + it;
+    const int64_t w = idx % N;
+    const int tr = int(idx / N);
+    const int64_t row = __ldg(win_start + w) + int64_t(t) * row_step;
+    const float2 kp = __ldg(reinterpret_cast<const float2*>(rows + row * 34 + 2 * v));
+    float x = 0.f, y = 0.f;
+    if (kp.x != 0.f) x = float(double(float(double(kp.x) - sc.center[2 * v])) / sc.scale[2 * v]);
+    if (kp.y != 0.f) y = float(double(float(double(kp.y) - sc.center[2 * v + 1])) / sc.scale[2 * v + 1]);
+    if (x != x) x = 0.f;   // np.where(np.isnan(X_scaled), 0.0, X_scaled)
+    if (y != y) y = 0.f;
+    const float* m = tb.m[tr];
+    out[(it * 2) * plane + p] = __fadd_rn(__fadd_rn(__fmul_rn(x, m[0]), __fmul_rn(y, m[1])), m[2]);
+    out[(it * 2 + 1) * plane + p] = __fadd_rn(__fadd_rn(__fmul_rn(x, m[3]), __fmul_rn(y, m[4])), m[5]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Bottleneck linear of the conditioning encoder: emb[n][l] = b[l] + sum_k h[n][k] * Wb[k][l]
 // h is planar-4 [n][C/4][P][4]; Wb was re-indexed at pack time to that order.  One warp / window.
 // ------------------------------------------------------------------------------------------

@@ -258,6 +258,74 @@ class ScoringEngine:
             scores[i0:i0 + n] = self.reverse_diffusion(items, n_generated_samples, seed=seed, first_window=i0)["best"]
         return scores.cpu()
 
+    # ------------------------------------------------------------------ f1: trajectory rows -> dataset items on the device
+    def normalize_frames(self, rows: torch.Tensor, vid_res: Sequence[float], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Bounding-box-centre coordinates of every frame row [F,34] (utils/data.py:165-187, 11-44); ``out`` may be ``rows``."""
+        F = rows.shape[0]
+        self._chk(rows, (F, 2 * N_JOINTS), "rows")
+        out = torch.empty_like(rows) if out is None else self._chk(out, (F, 2 * N_JOINTS), "out")
+        with torch.cuda.device(self.device):
+            check(self.lib.mcd_normalize_frames(self._h, rows.data_ptr(), F, float(vid_res[0]), float(vid_res[1]), out.data_ptr(),
+                                                self._stream()))
+        return out
+
+    def build_items(self, rows: torch.Tensor, win_start: torch.Tensor, center: np.ndarray, scale: np.ndarray, *,
+                    mats: Optional[np.ndarray] = None, first_item: int = 0, n_items: Optional[int] = None,
+                    row_step: int = 1) -> torch.Tensor:
+        """Dataset items ``first_item .. first_item + n_items - 1`` [n,2,seg_len,17] straight from the normalised frame rows:
+        window ``idx % N`` (rows ``win_start[w] + k * row_step``), robust-scaled, transform ``idx // N`` (``mats`` [K,6]; None =
+        the untransformed base windows).  utils/preprocessing.py:55-86, utils/data.py:345-354, utils/dataset.py:67-76, 241-256."""
+        F, N = rows.shape[0], win_start.shape[0]
+        self._chk(rows, (F, 2 * N_JOINTS), "rows")
+        if win_start.device != self.device or win_start.dtype != torch.int64 or not win_start.is_contiguous() or win_start.dim() != 1:
+            raise ValueError("win_start: need a contiguous 1-D int64 tensor on the engine's device")
+        center = np.ascontiguousarray(center, dtype=np.float64).reshape(2 * N_JOINTS)
+        scale = np.ascontiguousarray(scale, dtype=np.float64).reshape(2 * N_JOINTS)
+        K = 1
+        mats_p = None
+        if mats is not None:
+            mats = np.ascontiguousarray(mats, dtype=np.float32).reshape(-1, 6)
+            K, mats_p = mats.shape[0], mats.ctypes.data_as(_lib.c_float_p)
+        n_items = K * N - first_item if n_items is None else int(n_items)
+        out = self._new(n_items, N_COORDS, self.seg_len, N_JOINTS)
+        with torch.cuda.device(self.device):
+            check(self.lib.mcd_build_items(self._h, rows.data_ptr(), F, win_start.data_ptr(), N, int(row_step),
+                                           center.ctypes.data_as(_lib.c_double_p), scale.ctypes.data_as(_lib.c_double_p), mats_p, K,
+                                           int(first_item), n_items, out.data_ptr(), self._stream()))
+        return out
+
+    def score_trajectories_host(self, coords: np.ndarray, win_start: np.ndarray, center: np.ndarray, scale: np.ndarray,
+                                vid_res: Sequence[float], n_generated_samples: int, *, num_transform: int = 5, batch: int = 1024,
+                                seed: int = 0, row_step: int = 1, item_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+        """HOST in, HOST out from the parsed trajectory files: frame rows ``coords`` [F,34] (image coordinates) and the window
+        table ``win_start`` [N] (``mocodad_b200.ingest``) cross PCIe once; normalisation, windowing, scaling and the
+        ``num_transform`` transforms happen in HBM, batch by batch, in front of the reverse-diffusion loop.  Returns the 'best'
+        score of dataset items ``item_range`` (default: all ``num_transform * N``; a rank passes its shard) -- Philox noise is
+        keyed by the dataset index, so the scores do not depend on ``batch`` or on how the range is split across ranks."""
+        coords = np.ascontiguousarray(coords, dtype=np.float32)
+        win_start = np.ascontiguousarray(win_start, dtype=np.int64)
+        if coords.ndim != 2 or coords.shape[1] != 2 * N_JOINTS:
+            raise ValueError(f"coords: expected [F,{2 * N_JOINTS}], got {coords.shape}")
+        N, F = win_start.shape[0], coords.shape[0]
+        total = num_transform * N
+        lo, hi = (0, total) if item_range is None else (int(item_range[0]), int(item_range[1]))
+        if not 0 <= lo <= hi <= total:
+            raise ValueError(f"item_range {item_range} outside the dataset of {total} items")
+        if hi == lo:
+            return torch.empty(0, dtype=torch.float32)
+        if N and (win_start.min() < 0 or win_start.max() + (self.seg_len - 1) * row_step >= F):
+            raise ValueError("win_start: a window reaches outside the frame rows")
+        mats = pose_transform_matrices(num_transform)
+        d_rows = torch.from_numpy(coords).to(self.device, non_blocking=True)
+        d_start = torch.from_numpy(win_start).to(self.device, non_blocking=True)
+        self.normalize_frames(d_rows, vid_res, out=d_rows)
+        scores = torch.empty(hi - lo, dtype=torch.float32, device=self.device)
+        for i0 in range(lo, hi, batch):
+            n = min(batch, hi - i0)
+            items = self.build_items(d_rows, d_start, center, scale, mats=mats, first_item=i0, n_items=n, row_step=row_step)
+            scores[i0 - lo:i0 - lo + n] = self.reverse_diffusion(items, n_generated_samples, seed=seed, first_window=i0)["best"]
+        return scores.cpu()
+
     # ------------------------------------------------------------------ host-side tables
     def schedule(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         return schedule(self.N)
