@@ -21,6 +21,7 @@ import sys
 import threading
 import time
 
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -255,6 +256,41 @@ def run_b200(a):
               "GBps": round(2 * items.numel() * 4 / xf_s / 1e9, 1),
               "note": "dataset item = affine transform idx//N of base window idx%N (utils/dataset.py:67-76), built on the "
                       "device from base windows uploaded once; launch-latency-bound at this batch size"}
+
+    # ---- row f1, second slice: trajectory frame rows -> dataset items (normalise, window, scale, transform) in HBM -------
+    n_traj, traj_len = 256, 1024
+    gen = torch.Generator(device=dev).manual_seed(4242)
+    rows = (torch.rand(n_traj * traj_len, 34, device=dev, generator=gen) * 320.0 + 8.0).contiguous()
+    rows[torch.rand(rows.shape, device=dev, generator=gen) < 0.08] = 0.0
+    span = eng.seg_len
+    win_start = (torch.arange(n_traj, device=dev)[:, None] * traj_len + torch.arange(traj_len - span + 1, device=dev)[None, :]).reshape(-1).contiguous()
+    n_win = win_start.numel()
+    n_it = min(5 * n_win, 262144)
+    center, scale = np.zeros(34), np.full(34, 0.25)
+    norm = eng.normalize_frames(rows, (640.0, 360.0))
+    for _ in range(3):
+        eng.normalize_frames(rows, (640.0, 360.0), out=norm)
+        tr_items = eng.build_items(norm, win_start, center, scale, mats=mats, first_item=n_win - n_it // 2, n_items=n_it)
+    te = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    te[0].record()
+    for _ in range(10):
+        eng.normalize_frames(rows, (640.0, 360.0), out=norm)
+    te[1].record()
+    for _ in range(10):
+        tr_items = eng.build_items(norm, win_start, center, scale, mats=mats, first_item=n_win - n_it // 2, n_items=n_it)
+    te[2].record()
+    torch.cuda.synchronize(dev)
+    nf_s, bi_s = te[0].elapsed_time(te[1]) * 1e-4, te[1].elapsed_time(te[2]) * 1e-4
+    assert bool(torch.isfinite(tr_items).all())
+    ingest["trajectories"] = {
+        "frame_rows": rows.shape[0], "windows": n_win, "items_built": n_it,
+        "normalize_frames": {"rows_per_s": rows.shape[0] / nf_s, "GBps": round(2 * rows.numel() * 4 / nf_s / 1e9, 1)},
+        "build_items": {"items_per_s": n_it / bi_s, "GBps": round((tr_items.numel() + rows.numel()) * 4 / bi_s / 1e9, 1),
+                        "includes": "output tensor allocation by the caller (torch caching allocator)"},
+        "note": "reference on-disk trajectories (frame, 17 x,y) -> bounding-box-centre coordinates (utils/data.py:165-187) -> "
+                "sliding windows (utils/preprocessing.py:55-86) -> RobustScaler (utils/data.py:345-354) -> 5 transforms "
+                "(utils/dataset.py:67-76); frame rows cross PCIe once, no window tensor is materialised on the host"}
+    del rows, norm, tr_items, win_start
 
     # ---- per-kernel device times (CUDA events around every launch, one extra step) -----------
     eng.profile_enable(True)
