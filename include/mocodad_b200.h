@@ -153,16 +153,19 @@ MCD_API int mcd_expand_transforms(const mcd_model* m, const float* d_base, int64
  * compute_bounding_box (utils/data.py:11-44) for F frame rows [F,34] = (x1,y1,...,x17,y17) in image
  * coordinates; (0,0) marks a missing joint.  d_out [F,34] may alias d_rows.  Bit-identical to the
  * reference's float32 numpy arithmetic (numpy >= 2 promotion rules, as pinned by the oracle).
+ * With h_center / h_scale [34] (center_ / scale_ of the fitted RobustScaler; both NULL = off) the rows
+ * are also scaled (utils/data.py:345-354: zeros are missing and stay zero) -- the scaler acts per
+ * column, so scaling a row once equals scaling every window that contains it.
  * mcd_build_items: dataset item idx = first_item + i is transform idx / N of window idx % N
  * (utils/dataset.py:67-76); window w is rows d_win_start[w] + k * row_step, k < n_frames, of the
- * normalised frame array (utils/preprocessing.py:55-86), scaled by the fitted RobustScaler
- * (utils/data.py:345-354: zeros are missing and stay zero; h_center / h_scale [34] = center_ / scale_)
- * and laid out [2,n_frames,17] (utils/dataset.py:241-256).  h_mats [num_transform][6] as for
+ * frame array (utils/preprocessing.py:55-86), laid out [2,n_frames,17] (utils/dataset.py:241-256).
+ * h_center / h_scale: scale here (rows are unscaled bounding-box-centre coordinates) or NULL, NULL
+ * (rows were scaled by mcd_normalize_frames).  h_mats [num_transform][6] as for
  * mcd_expand_transforms (NULL = the identity, num_transform must be 1: the base windows).
  * d_win_start [N] int64 on the device; the caller guarantees every window lies inside [0,F).
  * d_out [n_items,2,n_frames,17]. */
 MCD_API int mcd_normalize_frames(const mcd_model* m, const float* d_rows, int64_t F, float vid_w, float vid_h,
-                         float* d_out, void* stream);
+                         const double* h_center, const double* h_scale, float* d_out, void* stream);
 MCD_API int mcd_build_items(const mcd_model* m, const float* d_rows, int64_t F, const int64_t* d_win_start, int64_t N,
                     int32_t row_step, const double* h_center, const double* h_scale, const float* h_mats,
                     int32_t num_transform, int64_t first_item, int64_t n_items, float* d_out, void* stream);

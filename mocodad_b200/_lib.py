@@ -57,7 +57,8 @@ SIGNATURES = {
     "mcd_pose_transform_matrix": (C.c_int, [C.c_int32, c_float_p]),
     "mcd_expand_transforms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_float_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p,
                                         C.c_void_p]),
-    "mcd_normalize_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "mcd_normalize_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, c_double_p, c_double_p, C.c_void_p,
+                                       C.c_void_p]),
     "mcd_build_items": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, c_double_p, c_double_p,
                                   c_float_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "mcd_window_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,

@@ -1088,17 +1088,39 @@ int mcd_expand_transforms(const mcd_model* m, const float* d_base, int64_t N, co
   return check_launch("expand_transforms");
 }
 
-int mcd_normalize_frames(const mcd_model* m, const float* d_rows, int64_t F, float vid_w, float vid_h, float* d_out, void* stream) {
+namespace {
+// center_ / scale_ of the fitted RobustScaler -> kernel parameter; both NULL = no scaling in this kernel
+int fill_scaler(const char* who, const double* h_center, const double* h_scale, ScalerTable* sc, int* apply) {
+  *apply = 0;
+  for (int k = 0; k < 34; ++k) { sc->center[k] = 0.0; sc->scale[k] = 1.0; }
+  if (h_center == nullptr && h_scale == nullptr) return MCD_OK;
+  if (h_center == nullptr || h_scale == nullptr) return fail(MCD_ERR_INVALID_ARG, "%s: center and scale must be given together", who);
+  for (int k = 0; k < 34; ++k) {
+    if (!(h_scale[k] != 0.0) || h_center[k] != h_center[k]) return fail(MCD_ERR_INVALID_ARG, "%s: scale[%d] is zero or NaN", who, k);
+    sc->center[k] = h_center[k];
+    sc->scale[k] = h_scale[k];
+  }
+  *apply = 1;
+  return MCD_OK;
+}
+}  // namespace
+
+int mcd_normalize_frames(const mcd_model* m, const float* d_rows, int64_t F, float vid_w, float vid_h, const double* h_center,
+                         const double* h_scale, float* d_out, void* stream) {
   MCD_TRY(check_ready(m));
-  if (d_rows == nullptr || d_out == nullptr || F < 0) return fail(MCD_ERR_INVALID_ARG, "mcd_normalize_frames: bad argument");
+  if (F < 0) return fail(MCD_ERR_INVALID_ARG, "mcd_normalize_frames: negative row count");
   if (!(vid_w >= 1.f) || !(vid_h >= 1.f)) return fail(MCD_ERR_INVALID_ARG, "mcd_normalize_frames: video resolution %g x %g", vid_w, vid_h);
+  ScalerTable sc{};
+  int apply = 0;
+  MCD_TRY(fill_scaler("mcd_normalize_frames", h_center, h_scale, &sc, &apply));
+  if (F == 0) return MCD_OK;
+  if (d_rows == nullptr || d_out == nullptr) return fail(MCD_ERR_INVALID_ARG, "mcd_normalize_frames: bad argument");
   if ((reinterpret_cast<uintptr_t>(d_rows) | reinterpret_cast<uintptr_t>(d_out)) & 7)
     return fail(MCD_ERR_INVALID_ARG, "mcd_normalize_frames: frame rows must be 8-byte aligned");
-  if (F == 0) return MCD_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   {
     LaunchScope ls(m, SLOT_NORM, F, s);
-    normalize_frames_kernel<<<grid_for(F * 32, kThreads, m->num_sms, 8), kThreads, 0, s>>>(d_rows, d_out, F, vid_w, vid_h);
+    normalize_frames_kernel<<<grid_for(F * 32, kThreads, m->num_sms, 8), kThreads, 0, s>>>(d_rows, d_out, F, vid_w, vid_h, sc, apply);
   }
   return check_launch("normalize_frames");
 }
@@ -1107,8 +1129,7 @@ int mcd_build_items(const mcd_model* m, const float* d_rows, int64_t F, const in
                     const double* h_center, const double* h_scale, const float* h_mats, int32_t num_transform, int64_t first_item,
                     int64_t n_items, float* d_out, void* stream) {
   MCD_TRY(check_ready(m));
-  if (d_rows == nullptr || d_win_start == nullptr || d_out == nullptr || h_center == nullptr || h_scale == nullptr || F < 1 || N < 1 ||
-      n_items < 0 || first_item < 0 || row_step < 1)
+  if (d_rows == nullptr || d_win_start == nullptr || F < 1 || N < 1 || n_items < 0 || first_item < 0 || row_step < 1)
     return fail(MCD_ERR_INVALID_ARG, "mcd_build_items: bad argument");
   if (reinterpret_cast<uintptr_t>(d_rows) & 7) return fail(MCD_ERR_INVALID_ARG, "mcd_build_items: frame rows must be 8-byte aligned");
   if (h_mats == nullptr && num_transform != 1) return fail(MCD_ERR_INVALID_ARG, "mcd_build_items: h_mats may be NULL only with one (identity) transform");
@@ -1120,13 +1141,11 @@ int mcd_build_items(const mcd_model* m, const float* d_rows, int64_t F, const in
   if (int64_t(m->cfg.n_frames - 1) * row_step + 1 > F)
     return fail(MCD_ERR_INVALID_ARG, "mcd_build_items: %lld frame rows cannot hold one window of %d rows, step %d", (long long)F,
                 m->cfg.n_frames, row_step);
-  if (n_items == 0) return MCD_OK;
   ScalerTable sc{};
-  for (int k = 0; k < 34; ++k) {
-    if (!(h_scale[k] != 0.0)) return fail(MCD_ERR_INVALID_ARG, "mcd_build_items: scale[%d] is zero or NaN", k);
-    sc.center[k] = h_center[k];
-    sc.scale[k] = h_scale[k];
-  }
+  int apply = 0;
+  MCD_TRY(fill_scaler("mcd_build_items", h_center, h_scale, &sc, &apply));
+  if (n_items == 0) return MCD_OK;
+  if (d_out == nullptr) return fail(MCD_ERR_INVALID_ARG, "mcd_build_items: d_out is NULL");
   TransformTable tb{};
   const float ident[6] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f};
   for (int t = 0; t < num_transform; ++t)
@@ -1134,8 +1153,9 @@ int mcd_build_items(const mcd_model* m, const float* d_rows, int64_t F, const in
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   {
     LaunchScope ls(m, SLOT_ITEMS, n_items, s);
-    build_items_kernel<<<grid_for(n_items * m->cfg.n_frames * 17, kThreads, m->num_sms, 8), kThreads, 0, s>>>(
-        d_rows, d_win_start, sc, tb, N, first_item, n_items, m->cfg.n_frames, row_step, d_out);
+    const int64_t chunks = (n_items + kItemsPerChunk - 1) / kItemsPerChunk;
+    build_items_kernel<<<grid_for(chunks, 1, m->num_sms, 16), kThreads, 0, s>>>(d_rows, d_win_start, sc, apply, tb, N, first_item, n_items,
+                                                                                 m->cfg.n_frames, row_step, d_out);
   }
   return check_launch("build_items");
 }

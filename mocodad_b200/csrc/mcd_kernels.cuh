@@ -672,12 +672,26 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ float clip_round(float v, float hi) {  // int(round(np.clip(v, 0, hi))): half to even
   return rintf(fminf(fmaxf(v, 0.f), hi));
 }
+// RobustScaler.transform on one normalised coordinate (utils/data.py:345-354): zeros are missing and stay zero; sklearn's
+// `X -= center_; X /= scale_` on float32 rows = one double operation each, rounded to float32 (equal to the float32 operation
+// when the fitted attribute is float32).
+struct ScalerTable {
+  double center[34], scale[34];
+};
+__device__ __forceinline__ float robust_scale(float v, double center, double scale) {
+  if (v == 0.f) return 0.f;
+  const float r = float(double(float(double(v) - center)) / scale);
+  return r != r ? 0.f : r;   // np.where(np.isnan(X_scaled), 0.0, X_scaled)
+}
 __global__ void __launch_bounds__(kThreads) normalize_frames_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t F,
-                                                                    float vid_w, float vid_h) {
+                                                                    float vid_w, float vid_h, const __grid_constant__ ScalerTable sc,
+                                                                    int apply_scaler) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t(gridDim.x) * kThreads) >> 5;
   const float inf = __int_as_float(0x7f800000);
   const float wl = __fsub_rn(vid_w, 1.f), hl = __fsub_rn(vid_h, 1.f);
+  const int col = lane < 17 ? 2 * lane : 0;
+  const double cx_s = sc.center[col], cy_s = sc.center[col + 1], sx_s = sc.scale[col], sy_s = sc.scale[col + 1];
   for (int64_t f = (blockIdx.x * int64_t(kThreads) + threadIdx.x) >> 5; f < F; f += warps) {
     float2 kp = make_float2(0.f, 0.f);
     if (lane < 17) kp = *reinterpret_cast<const float2*>(in + f * 34 + 2 * lane);
@@ -696,42 +710,51 @@ __global__ void __launch_bounds__(kThreads) normalize_frames_kernel(const float*
       if (bw != 0.f) ox = __fdiv_rn(__fsub_rn(hx ? kp.x : cx, cx), bw);            // data.py:178-182
       if (bh != 0.f) oy = __fdiv_rn(__fsub_rn(hy ? kp.y : cy, cy), bh);
     }
+    if (apply_scaler) {   // the scaler acts per column, so it commutes with the windowing: scale a row once, not once per item
+      ox = robust_scale(ox, cx_s, sx_s);
+      oy = robust_scale(oy, cy_s, sy_s);
+    }
     if (lane < 17) *reinterpret_cast<float2*>(out + f * 34 + 2 * lane) = make_float2(ox, oy);
   }
 }
 
 // build_items_kernel: dataset item idx = first_item + i is transform idx / N of window idx % N (utils/dataset.py:67-76), the
 // window being rows start, start + step, ... of the normalised frame array (utils/preprocessing.py:55-86), robust-scaled
-// (utils/data.py:345-354: 0 -> missing -> 0; sklearn's `X -= center_; X /= scale_` on float32 rows, each a double operation
-// rounded to float32, which equals the float32 operation when the attribute is float32), laid out [2, L, 17]
-// (utils/dataset.py:241-256) and transformed like expand_transforms_kernel.  No window tensor is ever materialised: a frame row
-// is read from L2 by the up to L x num_transform items that share it.
-struct ScalerTable {
-  double center[34], scale[34];
-};
+// here (apply_scaler) or already in normalize_frames_kernel, laid out [2, L, 17] (utils/dataset.py:241-256) and transformed
+// like expand_transforms_kernel.  No window tensor is ever materialised: a frame row is read from L2 by the up to
+// L x num_transform items that share it.  A CTA builds kItemsPerChunk consecutive items (one contiguous output span,
+// coalesced stores); the 64-bit item -> (transform, window) split happens once per chunk, the rest is 32-bit arithmetic.
+constexpr int kItemsPerChunk = 8;
 __global__ void __launch_bounds__(kThreads) build_items_kernel(const float* __restrict__ rows, const int64_t* __restrict__ win_start,
-                                                               const __grid_constant__ ScalerTable sc,
+                                                               const __grid_constant__ ScalerTable sc, int apply_scaler,
                                                                const __grid_constant__ TransformTable tb, int64_t N, int64_t first_item,
                                                                int64_t n_items, int seg_len, int row_step, float* __restrict__ out) {
   const int plane = seg_len * 17;
-  const int64_t total = n_items * plane;
-  for (int64_t i = blockIdx.x * int64_t(kThreads) + threadIdx.x; i < total; i += int64_t(gridDim.x) * kThreads) {
-    const int64_t it = i / plane;
-    const int p = int(i - it * plane);
-    const int t = p / 17, v = p - t * 17;
-    const int64_t idx = first_item + it;
-    const int64_t w = idx % N;
-    const int tr = int(idx / N);
-    const int64_t row = __ldg(win_start + w) + int64_t(t) * row_step;
-    const float2 kp = __ldg(reinterpret_cast<const float2*>(rows + row * 34 + 2 * v));
-    float x = 0.f, y = 0.f;
-    if (kp.x != 0.f) x = float(double(float(double(kp.x) - sc.center[2 * v])) / sc.scale[2 * v]);
-    if (kp.y != 0.f) y = float(double(float(double(kp.y) - sc.center[2 * v + 1])) / sc.scale[2 * v + 1]);
-    if (x != x) x = 0.f;   // np.where(np.isnan(X_scaled), 0.0, X_scaled)
-    if (y != y) y = 0.f;
-    const float* m = tb.m[tr];
-    out[(it * 2) * plane + p] = __fadd_rn(__fadd_rn(__fmul_rn(x, m[0]), __fmul_rn(y, m[1])), m[2]);
-    out[(it * 2 + 1) * plane + p] = __fadd_rn(__fadd_rn(__fmul_rn(x, m[3]), __fmul_rn(y, m[4])), m[5]);
+  const int64_t n_chunks = (n_items + kItemsPerChunk - 1) / kItemsPerChunk;
+  for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    const int64_t it0 = ch * kItemsPerChunk;
+    const int cnt = int(n_items - it0 < kItemsPerChunk ? n_items - it0 : kItemsPerChunk);
+    const int64_t idx0 = first_item + it0;
+    const int tr0 = int(idx0 / N);
+    const int64_t w0 = idx0 - tr0 * N;
+    float* dst = out + it0 * 2 * plane;
+    for (int j = threadIdx.x; j < cnt * plane; j += kThreads) {
+      const int il = j / plane, p = j - il * plane;
+      const int t = p / 17, v = p - t * 17;
+      int64_t w = w0 + il;
+      int tr = tr0;
+      while (w >= N) { w -= N; ++tr; }
+      const int64_t row = __ldg(win_start + w) + int64_t(t) * row_step;
+      const float2 kp = __ldg(reinterpret_cast<const float2*>(rows + row * 34 + 2 * v));
+      float x = kp.x, y = kp.y;
+      if (apply_scaler) {
+        x = robust_scale(x, sc.center[2 * v], sc.scale[2 * v]);
+        y = robust_scale(y, sc.center[2 * v + 1], sc.scale[2 * v + 1]);
+      }
+      const float* m = tb.m[tr];
+      dst[(il * 2) * plane + p] = __fadd_rn(__fadd_rn(__fmul_rn(x, m[0]), __fmul_rn(y, m[1])), m[2]);
+      dst[(il * 2 + 1) * plane + p] = __fadd_rn(__fadd_rn(__fmul_rn(x, m[3]), __fmul_rn(y, m[4])), m[5]);
+    }
   }
 }
 

@@ -259,38 +259,51 @@ class ScoringEngine:
         return scores.cpu()
 
     # ------------------------------------------------------------------ f1: trajectory rows -> dataset items on the device
-    def normalize_frames(self, rows: torch.Tensor, vid_res: Sequence[float], out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Bounding-box-centre coordinates of every frame row [F,34] (utils/data.py:165-187, 11-44); ``out`` may be ``rows``."""
+    @staticmethod
+    def _scaler_ptrs(center, scale):
+        if center is None and scale is None:
+            return None, None, None
+        if center is None or scale is None:
+            raise ValueError("center and scale must be given together")
+        center = np.ascontiguousarray(center, dtype=np.float64).reshape(2 * N_JOINTS)
+        scale = np.ascontiguousarray(scale, dtype=np.float64).reshape(2 * N_JOINTS)
+        return center.ctypes.data_as(_lib.c_double_p), scale.ctypes.data_as(_lib.c_double_p), (center, scale)
+
+    def normalize_frames(self, rows: torch.Tensor, vid_res: Sequence[float], out: Optional[torch.Tensor] = None, *,
+                         center: Optional[np.ndarray] = None, scale: Optional[np.ndarray] = None) -> torch.Tensor:
+        """Bounding-box-centre coordinates of every frame row [F,34] (utils/data.py:165-187, 11-44); ``out`` may be ``rows``.
+        With ``center`` / ``scale`` (the fitted RobustScaler's ``center_`` / ``scale_``) the rows are robust-scaled as well
+        (utils/data.py:345-354) -- once per row instead of once per window that contains it."""
         F = rows.shape[0]
         self._chk(rows, (F, 2 * N_JOINTS), "rows")
         out = torch.empty_like(rows) if out is None else self._chk(out, (F, 2 * N_JOINTS), "out")
+        cp, sp, _keep = self._scaler_ptrs(center, scale)
         with torch.cuda.device(self.device):
-            check(self.lib.mcd_normalize_frames(self._h, rows.data_ptr(), F, float(vid_res[0]), float(vid_res[1]), out.data_ptr(),
-                                                self._stream()))
+            check(self.lib.mcd_normalize_frames(self._h, rows.data_ptr(), F, float(vid_res[0]), float(vid_res[1]), cp, sp,
+                                                out.data_ptr(), self._stream()))
         return out
 
-    def build_items(self, rows: torch.Tensor, win_start: torch.Tensor, center: np.ndarray, scale: np.ndarray, *,
-                    mats: Optional[np.ndarray] = None, first_item: int = 0, n_items: Optional[int] = None,
-                    row_step: int = 1) -> torch.Tensor:
+    def build_items(self, rows: torch.Tensor, win_start: torch.Tensor, center: Optional[np.ndarray] = None,
+                    scale: Optional[np.ndarray] = None, *, mats: Optional[np.ndarray] = None, first_item: int = 0,
+                    n_items: Optional[int] = None, row_step: int = 1) -> torch.Tensor:
         """Dataset items ``first_item .. first_item + n_items - 1`` [n,2,seg_len,17] straight from the normalised frame rows:
-        window ``idx % N`` (rows ``win_start[w] + k * row_step``), robust-scaled, transform ``idx // N`` (``mats`` [K,6]; None =
-        the untransformed base windows).  utils/preprocessing.py:55-86, utils/data.py:345-354, utils/dataset.py:67-76, 241-256."""
+        window ``idx % N`` (rows ``win_start[w] + k * row_step``), robust-scaled here (``center`` / ``scale`` given) or already by
+        ``normalize_frames``, transform ``idx // N`` (``mats`` [K,6]; None = the untransformed base windows).
+        utils/preprocessing.py:55-86, utils/data.py:345-354, utils/dataset.py:67-76, 241-256."""
         F, N = rows.shape[0], win_start.shape[0]
         self._chk(rows, (F, 2 * N_JOINTS), "rows")
         if win_start.device != self.device or win_start.dtype != torch.int64 or not win_start.is_contiguous() or win_start.dim() != 1:
             raise ValueError("win_start: need a contiguous 1-D int64 tensor on the engine's device")
-        center = np.ascontiguousarray(center, dtype=np.float64).reshape(2 * N_JOINTS)
-        scale = np.ascontiguousarray(scale, dtype=np.float64).reshape(2 * N_JOINTS)
+        cp, sp, _keep = self._scaler_ptrs(center, scale)
         K = 1
         mats_p = None
         if mats is not None:
             mats = np.ascontiguousarray(mats, dtype=np.float32).reshape(-1, 6)
             K, mats_p = mats.shape[0], mats.ctypes.data_as(_lib.c_float_p)
         n_items = K * N - first_item if n_items is None else int(n_items)
-        out = self._new(n_items, N_COORDS, self.seg_len, N_JOINTS)
+        out = self._new(max(n_items, 0), N_COORDS, self.seg_len, N_JOINTS)
         with torch.cuda.device(self.device):
-            check(self.lib.mcd_build_items(self._h, rows.data_ptr(), F, win_start.data_ptr(), N, int(row_step),
-                                           center.ctypes.data_as(_lib.c_double_p), scale.ctypes.data_as(_lib.c_double_p), mats_p, K,
+            check(self.lib.mcd_build_items(self._h, rows.data_ptr(), F, win_start.data_ptr(), N, int(row_step), cp, sp, mats_p, K,
                                            int(first_item), n_items, out.data_ptr(), self._stream()))
         return out
 
@@ -318,11 +331,11 @@ class ScoringEngine:
         mats = pose_transform_matrices(num_transform)
         d_rows = torch.from_numpy(coords).to(self.device, non_blocking=True)
         d_start = torch.from_numpy(win_start).to(self.device, non_blocking=True)
-        self.normalize_frames(d_rows, vid_res, out=d_rows)
+        self.normalize_frames(d_rows, vid_res, out=d_rows, center=center, scale=scale)   # normalised + scaled, in place
         scores = torch.empty(hi - lo, dtype=torch.float32, device=self.device)
         for i0 in range(lo, hi, batch):
             n = min(batch, hi - i0)
-            items = self.build_items(d_rows, d_start, center, scale, mats=mats, first_item=i0, n_items=n, row_step=row_step)
+            items = self.build_items(d_rows, d_start, mats=mats, first_item=i0, n_items=n, row_step=row_step)
             scores[i0 - lo:i0 - lo + n] = self.reverse_diffusion(items, n_generated_samples, seed=seed, first_window=i0)["best"]
         return scores.cpu()
 

@@ -393,6 +393,40 @@ class MoCoDAD(_Base):
         print(f'AUC score: {auc_score:.6f}')
         return auc_score
 
+    def score_trajectories(self, data_dir: str, vid_res, split: str = None, batch: int = 1024):
+        """The test epoch straight from the reference's on-disk trajectories, bypassing the host
+        dataset: what ``get_dataset_and_loader`` (utils/dataset.py:270-331 -> PoseDatasetRobust) + ``trainer.test`` produce,
+        with the frame rows uploaded once and every dataset item built in HBM (``ScoringEngine.score_trajectories_host``).
+        Needs ``{ckpt_dir}/local_robust.pickle`` like the reference's test split (get_robust_data.py:115-127).  Under an
+        initialised ``torch.distributed`` group every rank scores its contiguous shard of the dataset index space and one
+        all-gather assembles the scores.  Returns (loss [K*N], trans [K*N], meta [K*N,4], frames [K*N,seg_len]) as numpy,
+        in dataset order -- the inputs of ``post_processing``."""
+        from . import ingest, sharding
+        import torch.distributed as dist
+        if self.aggregation_strategy != 'best':
+            raise NotImplementedError("score_trajectories returns the 'best' aggregation (every shipped test config); use "
+                                      "forward() on batches for the other strategies")
+        split = self.split if split is None else split
+        ts = ingest.load_trajectories(os.path.join(data_dir, ingest.split_subfolder(split), 'trajectories'))
+        starts, meta, frames = ingest.window_table(ts, self.n_frames, 1)       # no strides for the test set (dataset.py:308)
+        center, scale = ingest.load_robust_scaler(self.ckpt_dir)
+        K, N = max(int(self.num_transforms), 1), len(starts)
+        total = K * N
+        rank, world = (dist.get_rank(), dist.get_world_size()) if (dist.is_available() and dist.is_initialized()) else (0, 1)
+        lo, hi = sharding.shard_bounds(total, rank, world)
+        local = self.engine().score_trajectories_host(ts.coords, starts, center, scale, vid_res, self.n_generated_samples,
+                                                      num_transform=K, batch=batch, seed=self.seed, item_range=(lo, hi))
+        scores = sharding.gather_scores(local.to(self.device), total).cpu().numpy() if world > 1 else local.numpy()
+        trans = np.repeat(np.arange(K, dtype=np.int64), N)                     # item idx -> idx // N (dataset.py:70-72)
+        return scores, trans, np.tile(meta, (K, 1)), np.tile(frames, (K, 1))
+
+    def test_on_trajectories(self, data_dir: str, vid_res, split: str = None, batch: int = 1024) -> float:
+        """``score_trajectories`` -> ``post_processing`` -> AUC: the device-ingest twin of eval_MoCoDAD.py:30-38."""
+        scores, trans, meta, frames = self.score_trajectories(data_dir, vid_res, split=split, batch=batch)
+        auc_score = self.post_processing(scores, None, trans, meta, frames)
+        self.log('AUC', auc_score)
+        return auc_score
+
     def _load_tensors(self, split_name: str, aggr_strategy: str, n_gen: int) -> Dict[str, torch.Tensor]:
         """mocodad.py:583-603"""
         path = os.path.join(self.ckpt_dir, 'saved_tensors_{}_{}_{}'.format(split_name, aggr_strategy, n_gen))

@@ -122,6 +122,13 @@ def test_build_items_vs_reference_fixture(tag, seg_len, stride, sfx):
         eng.build_items(rows, d_start, g["center"], g["scale"], mats=mats, first_item=5 * n - 1, n_items=2, row_step=stride)
     with pytest.raises(Exception):
         eng.build_items(rows, d_start, g["center"], np.zeros(34), row_step=stride)
+    # scaler fused into the normalisation (one pass over the rows) + pure gather: same bits
+    scaled = eng.normalize_frames(torch.from_numpy(ts.coords).cuda(), g["vid_res"], center=g["center"], scale=g["scale"])
+    assert np.array_equal(eng.build_items(scaled, d_start, row_step=stride).cpu().numpy(), base)
+    assert np.array_equal(eng.build_items(scaled, d_start, mats=mats, row_step=stride).cpu().numpy(), items)
+    odd = eng.build_items(scaled, d_start, mats=mats, first_item=1, n_items=5 * n - 2, row_step=stride)   # chunk tails, N not a multiple of 8
+    assert np.array_equal(odd.cpu().numpy(), items[1:5 * n - 1])
+    assert eng.build_items(scaled, d_start, mats=mats, first_item=3, n_items=0, row_step=stride).shape == (0, 2, seg_len, 17)
 
 
 @pytest.mark.gpu
@@ -143,3 +150,58 @@ def test_score_trajectories_host_equals_scoring_the_materialised_dataset():
     assert torch.equal(shard, want[lo:hi])
     with pytest.raises(ValueError):
         eng.score_trajectories_host(ts.coords, starts + 10_000, g["center"], g["scale"], g["vid_res"], 2)
+
+
+@pytest.mark.gpu
+def test_module_scores_a_trajectory_tree_like_the_batch_path(tmp_path):
+    """MoCoDAD.test_on_trajectories (data dir -> AUC, items built in HBM) == forward() over the materialised dataset."""
+    import argparse
+    import pickle
+    from sklearn.preprocessing import RobustScaler
+    from mocodad_b200 import MoCoDAD, synthetic as synth
+    from test_module import BASE
+    g = np.load(GOLD)
+    ts = _ts(g, "")
+    # the reference's on-disk layout: {data_dir}/testing/trajectories/{scene}-{clip}/{person}.csv, {ckpt_dir}/local_robust.pickle, gt masks
+    data_dir, ckpt_dir, gt_dir = tmp_path / "data", tmp_path / "ckpt", tmp_path / "gt"
+    ckpt_dir.mkdir()
+    gt_dir.mkdir()
+    row0 = 0
+    rng = np.random.default_rng(2)
+    for k, n in enumerate(ts.lengths):
+        scene, clip, person = (int(v) for v in ts.ids[k])
+        folder = data_dir / "testing" / "trajectories" / f"{scene:02d}-{clip:04d}"
+        folder.mkdir(parents=True, exist_ok=True)
+        rows = np.concatenate([ts.frames[row0:row0 + n, None].astype(np.float64), ts.coords[row0:row0 + n].astype(np.float64)], axis=1)
+        np.savetxt(folder / f"{person:04d}.csv", rows, delimiter=",", fmt=["%d"] + ["%.2f"] * 34)
+        np.save(gt_dir / f"{scene:02d}_{clip:04d}.npy", (rng.random(int(ts.frames.max()) + 8) < 0.3).astype(np.int64))
+        row0 += n
+    sk = RobustScaler(quantile_range=(10.0, 90.0))
+    sk.center_, sk.scale_ = g["center"].astype(np.float32), g["scale"]
+    with open(ckpt_dir / "local_robust.pickle", "wb") as fh:
+        pickle.dump(sk, fh)
+    cfg = dict(BASE, noise_steps=4, n_generated_samples=2, gt_path=str(gt_dir), ckpt_dir=str(ckpt_dir), dataset_choice="HR-STC",
+               pad_size=3, filter_kernel_size=5, frames_shift=2)
+    model = MoCoDAD(argparse.Namespace(**cfg))
+    model.load_state_dict(synth.synth_state_dict(synth.state_dict_spec(T=3, T_cond=3), seed=0))
+    model = model.to("cuda:0")
+    scores, trans, meta, frames = model.score_trajectories(str(data_dir), g["vid_res"], batch=100)
+    # the directory walk may visit trajectories in another order than the fixture: compare through the window identity
+    ts2 = ingest.load_trajectories(str(data_dir / "testing" / "trajectories"))
+    starts2, meta2, frames2 = ingest.window_table(ts2, 6, 1)
+    n = len(starts2)
+    assert scores.shape == (5 * n,) and np.array_equal(meta[:n], meta2) and np.array_equal(frames[n:2 * n], frames2)
+    assert np.array_equal(trans, np.repeat(np.arange(5), n))
+    base = otr.base_windows(ts2.coords, starts2, 6, 1, g["center"], g["scale"], g["vid_res"])[:, :2]
+    eng = model.engine()
+    from mocodad_b200.engine import pose_transform_matrices
+    items = eng.expand_transforms(torch.from_numpy(np.ascontiguousarray(base)).cuda(), pose_transform_matrices(5), 0, 5 * n)
+    model.on_test_epoch_start()
+    for i0 in range(0, 5 * n, 64):
+        sl = slice(i0, min(i0 + 64, 5 * n))
+        model.test_step([items[sl], torch.from_numpy(trans[sl]), torch.from_numpy(meta[sl]), torch.from_numpy(frames[sl])], 0)
+    want = np.concatenate([o[0].cpu().numpy() for o in model._test_output_list])
+    assert np.array_equal(scores, want)
+    auc_batches = model.on_test_epoch_end()
+    auc = model.test_on_trajectories(str(data_dir), g["vid_res"], batch=77)
+    assert 0.0 <= auc <= 1.0 and auc == auc_batches
