@@ -258,7 +258,7 @@ def run_b200(a):
                       "device from base windows uploaded once; launch-latency-bound at this batch size"}
 
     # ---- row f1, second slice: trajectory frame rows -> dataset items (normalise, window, scale, transform) in HBM -------
-    n_traj, traj_len = 256, 1024
+    n_traj, traj_len = 1024, 1024
     gen = torch.Generator(device=dev).manual_seed(4242)
     rows = (torch.rand(n_traj * traj_len, 34, device=dev, generator=gen) * 320.0 + 8.0).contiguous()
     rows[torch.rand(rows.shape, device=dev, generator=gen) < 0.08] = 0.0

@@ -1120,7 +1120,7 @@ int mcd_normalize_frames(const mcd_model* m, const float* d_rows, int64_t F, flo
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   {
     LaunchScope ls(m, SLOT_NORM, F, s);
-    normalize_frames_kernel<<<grid_for(F * 32, kThreads, m->num_sms, 8), kThreads, 0, s>>>(d_rows, d_out, F, vid_w, vid_h, sc, apply);
+    normalize_frames_kernel<<<grid_for(F, kNormRows, m->num_sms, 6), kThreads, 0, s>>>(d_rows, d_out, F, vid_w, vid_h, sc, apply);
   }
   return check_launch("normalize_frames");
 }

@@ -654,21 +654,11 @@ __global__ void __launch_bounds__(kThreads) expand_transforms_kernel(const float
 // Window ingest (second slice): raw trajectory rows -> dataset items, on the device.
 //
 // normalize_frames_kernel: Trajectory._from_image_to_centre_bounding_box (utils/data.py:165-187) with
-// compute_bounding_box (utils/data.py:11-44) for every frame row [34] = (x1, y1, ..., x17, y17).  One warp per frame:
-// lane v < 17 owns joint v (one coalesced 8-byte load per lane), the box is four warp-shuffle min / max reductions over the
-// non-zero coordinates.  The reference computes in float32 with every operation rounded separately (numpy scalars,
-// Python ints for the rounded corners), so every step below is an explicit _rn intrinsic -- no FMA contraction.
+// compute_bounding_box (utils/data.py:11-44) for every frame row [34] = (x1, y1, ..., x17, y17).  HBM-bound (272 B per
+// row): rows are staged through shared memory in contiguous tiles and one thread owns one row.  The reference computes in
+// float32 with every operation rounded separately (numpy scalars, Python ints for the rounded corners), so every step below
+// is an explicit _rn intrinsic -- no FMA contraction.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float warp_min(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
 __device__ __forceinline__ float clip_round(float v, float hi) {  // int(round(np.clip(v, 0, hi))): half to even
   return rintf(fminf(fmaxf(v, 0.f), hi));
 }
@@ -683,38 +673,59 @@ __device__ __forceinline__ float robust_scale(float v, double center, double sca
   const float r = float(double(float(double(v) - center)) / scale);
   return r != r ? 0.f : r;   // np.where(np.isnan(X_scaled), 0.0, X_scaled)
 }
-__global__ void __launch_bounds__(kThreads) normalize_frames_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t F,
-                                                                    float vid_w, float vid_h, const __grid_constant__ ScalerTable sc,
-                                                                    int apply_scaler) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warps = (int64_t(gridDim.x) * kThreads) >> 5;
+constexpr int kNormRows = kThreads;  // frame rows per CTA tile: one per thread
+__global__ void __launch_bounds__(kThreads) normalize_frames_kernel(const float* in, float* out, int64_t F, float vid_w, float vid_h,
+                                                                    const __grid_constant__ ScalerTable sc, int apply_scaler) {
+  // A tile of kNormRows rows (one contiguous 34 KB span) is staged with coalesced 8-byte copies; thread r then owns row r:
+  // its 17 (x, y) pairs sit at 8-byte words 17 r + j, which is conflict-free across the 16 lanes of a 64-bit shared-memory
+  // phase.  Results go back through the same tile, so `out` may alias `in` (a tile is read completely before it is written
+  // and no other CTA touches it).
+  __shared__ __align__(16) float2 tile[kNormRows * 17];
   const float inf = __int_as_float(0x7f800000);
   const float wl = __fsub_rn(vid_w, 1.f), hl = __fsub_rn(vid_h, 1.f);
-  const int col = lane < 17 ? 2 * lane : 0;
-  const double cx_s = sc.center[col], cy_s = sc.center[col + 1], sx_s = sc.scale[col], sy_s = sc.scale[col + 1];
-  for (int64_t f = (blockIdx.x * int64_t(kThreads) + threadIdx.x) >> 5; f < F; f += warps) {
-    float2 kp = make_float2(0.f, 0.f);
-    if (lane < 17) kp = *reinterpret_cast<const float2*>(in + f * 34 + 2 * lane);
-    const bool hx = kp.x != 0.f, hy = kp.y != 0.f;   // zeros are missing coordinates (data.py:27)
-    const float left = warp_min(hx ? kp.x : inf), right = warp_max(hx ? kp.x : -inf);
-    const float top = warp_min(hy ? kp.y : inf), bottom = warp_max(hy ? kp.y : -inf);
-    float ox = 0.f, oy = 0.f;
-    // no non-zero x or no non-zero y: np.min raises -> box (0,0,0,0) -> zero width and height -> zeros (data.py:28-32, 182-183)
-    if (left <= right && top <= bottom) {
-      const float ew = __fmul_rn(0.1f, __fadd_rn(__fsub_rn(right, left), 1.f));   // data.py:34
-      const float eh = __fmul_rn(0.1f, __fadd_rn(__fsub_rn(bottom, top), 1.f));
-      const float L = clip_round(__fsub_rn(left, ew), wl), R = clip_round(__fadd_rn(right, ew), wl);   // data.py:35-41
-      const float T = clip_round(__fsub_rn(top, eh), hl), B = clip_round(__fadd_rn(bottom, eh), hl);
-      const float cx = __fmul_rn(__fadd_rn(L, R), 0.5f), cy = __fmul_rn(__fadd_rn(T, B), 0.5f);     // exact: small integers
-      const float bw = __fsub_rn(R, L), bh = __fsub_rn(B, T);
-      if (bw != 0.f) ox = __fdiv_rn(__fsub_rn(hx ? kp.x : cx, cx), bw);            // data.py:178-182
-      if (bh != 0.f) oy = __fdiv_rn(__fsub_rn(hy ? kp.y : cy, cy), bh);
+  const int64_t n_tiles = (F + kNormRows - 1) / kNormRows;
+  for (int64_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+    const int64_t f0 = tl * kNormRows;
+    const int nrows = int(F - f0 < kNormRows ? F - f0 : kNormRows);
+    const float2* src = reinterpret_cast<const float2*>(in + f0 * 34);
+    float2* dst = reinterpret_cast<float2*>(out + f0 * 34);
+    for (int k = threadIdx.x; k < 17 * nrows; k += kThreads) tile[k] = src[k];
+    __syncthreads();
+    if (int(threadIdx.x) < nrows) {
+      float2* r = tile + 17 * threadIdx.x;
+      float left = inf, right = -inf, top = inf, bottom = -inf;   // over the non-zero coordinates (data.py:27-29)
+#pragma unroll
+      for (int j = 0; j < 17; ++j) {
+        const float2 kp = r[j];
+        if (kp.x != 0.f) { left = fminf(left, kp.x); right = fmaxf(right, kp.x); }
+        if (kp.y != 0.f) { top = fminf(top, kp.y); bottom = fmaxf(bottom, kp.y); }
+      }
+      // no non-zero x or no non-zero y: np.min raises -> box (0,0,0,0) -> zero width and height -> zeros (data.py:28-32, 182-183)
+      float cx = 0.f, cy = 0.f, bw = 0.f, bh = 0.f;
+      if (left <= right && top <= bottom) {
+        const float ew = __fmul_rn(0.1f, __fadd_rn(__fsub_rn(right, left), 1.f));   // data.py:34
+        const float eh = __fmul_rn(0.1f, __fadd_rn(__fsub_rn(bottom, top), 1.f));
+        const float L = clip_round(__fsub_rn(left, ew), wl), R = clip_round(__fadd_rn(right, ew), wl);   // data.py:35-41
+        const float T = clip_round(__fsub_rn(top, eh), hl), B = clip_round(__fadd_rn(bottom, eh), hl);
+        cx = __fmul_rn(__fadd_rn(L, R), 0.5f), cy = __fmul_rn(__fadd_rn(T, B), 0.5f);               // exact: small integers
+        bw = __fsub_rn(R, L), bh = __fsub_rn(B, T);
+      }
+#pragma unroll 1
+      for (int j = 0; j < 17; ++j) {
+        const float2 kp = r[j];
+        float ox = 0.f, oy = 0.f;
+        if (bw != 0.f) ox = __fdiv_rn(__fsub_rn(kp.x != 0.f ? kp.x : cx, cx), bw);   // data.py:178-182
+        if (bh != 0.f) oy = __fdiv_rn(__fsub_rn(kp.y != 0.f ? kp.y : cy, cy), bh);
+        if (apply_scaler) {   // the scaler acts per column, so it commutes with the windowing: scale a row once, not once per item
+          ox = robust_scale(ox, sc.center[2 * j], sc.scale[2 * j]);
+          oy = robust_scale(oy, sc.center[2 * j + 1], sc.scale[2 * j + 1]);
+        }
+        r[j] = make_float2(ox, oy);
+      }
     }
-    if (apply_scaler) {   // the scaler acts per column, so it commutes with the windowing: scale a row once, not once per item
-      ox = robust_scale(ox, cx_s, sx_s);
-      oy = robust_scale(oy, cy_s, sy_s);
-    }
-    if (lane < 17) *reinterpret_cast<float2*>(out + f * 34 + 2 * lane) = make_float2(ox, oy);
+    __syncthreads();
+    for (int k = threadIdx.x; k < 17 * nrows; k += kThreads) dst[k] = tile[k];
+    __syncthreads();
   }
 }
 
