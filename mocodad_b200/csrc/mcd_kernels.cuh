@@ -749,8 +749,12 @@ __global__ void __launch_bounds__(kThreads) build_items_kernel(const float* __re
     const int tr0 = int(idx0 / N);
     const int64_t w0 = idx0 - tr0 * N;
     float* dst = out + it0 * 2 * plane;
-    for (int j = threadIdx.x; j < cnt * plane; j += kThreads) {
-      const int il = j / plane, p = j - il * plane;
+    // (item in the chunk, position in the item) advance incrementally: no per-element division by the runtime `plane`
+    int il = 0, p = threadIdx.x;
+    while (p >= plane) { p -= plane; ++il; }
+    for (; il < cnt; p += kThreads) {
+      while (p >= plane) { p -= plane; ++il; }
+      if (il >= cnt) break;
       const int t = p / 17, v = p - t * 17;
       int64_t w = w0 + il;
       int tr = tr0;
