@@ -42,6 +42,7 @@ def parse_args():
     p.add_argument("--noise-steps", type=int, default=10)
     p.add_argument("--gen", type=int, default=50, help="n_generated_samples")
     p.add_argument("--cpu-sample", default="128x5", help="cpu_baseline sample: windows x samples")
+    p.add_argument("--eager-samples", type=int, default=5, help="generated samples timed by the PyTorch CUDA-eager baseline arm")
     p.add_argument("--ref-sample", default="32x5", help="--impl reference: windows x samples per step")
     p.add_argument("--no-cpu-baseline", action="store_true")
     return p.parse_args()
@@ -132,6 +133,40 @@ def cpu_reference_rate(a, n_windows: int, n_samples: int, steps: int, warmup: in
     dt = (time.perf_counter() - t0) / max(steps, 1)
     window_steps_per_s = n_windows * n_samples * (a.noise_steps - 1) / dt
     return window_steps_per_s / (a.gen * (a.noise_steps - 1)), dt
+
+
+def cuda_eager_reference_rate(a, dev, n_samples: int, steps: int = 2, warmup: int = 1):
+    """The baseline leg's second arm: oracle/ref_port.py -- the reference's own ATen operators (einsum / conv2d / batch_norm /
+    prelu / linear, with its permutes and copies) in the reference's order -- run as PyTorch CUDA eager on this GPU, at the
+    workload's batch size, on ``n_samples`` of the G generated samples (the samples are sequential in the reference, so the time
+    scales linearly).  This is the denominator of north_star's ">= 10x the reference PyTorch-CUDA path"; /root/reference does
+    not exist on the GPU box, and the port omits the reference's per-step host->device schedule uploads, so the
+    figure favours the reference.  Returns (equivalent windows/s at G samples, seconds per step, launches unknown)."""
+    from mocodad_b200 import synthetic as synth
+    from oracle import ref_port
+    T = a.seg_len - 3
+    sd = {k: v.to(dev) for k, v in synth.synth_state_dict(synth.state_dict_spec(T=T, T_cond=3), seed=0).items()}
+    data = synth.synth_batch(a.batch, a.seg_len, seed=1)[0].to(dev)
+
+    def one():
+        with torch.no_grad(), torch.device(dev):
+            loss, _ = ref_port.reverse_diffusion(sd, data, noise_steps=a.noise_steps, n_generated_samples=n_samples,
+                                                 randn_like=torch.randn_like)
+        return loss
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        loss = one()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    wall = (time.perf_counter() - t0) / steps
+    assert loss.is_cuda and bool(torch.isfinite(loss).all())
+    dt = max(e0.elapsed_time(e1) * 1e-3 / steps, wall)
+    return a.batch * n_samples / dt / a.gen, dt
 
 
 def run_reference(a):
@@ -368,6 +403,16 @@ def run_b200(a):
         cpu_baseline = {"value": cv, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                         "sample": f"oracle/ref_port.py (the reference's torch CPU operators): {nw} windows x {ns} samples x "
                                   f"{N - 1} steps in {cdt:.1f} s, scaled to {G} samples/window"}
+        try:
+            ns_e = max(1, min(G, a.eager_samples))
+            ev, edt = cuda_eager_reference_rate(a, dev, ns_e)
+            cpu_baseline["reference_cuda_eager"] = {
+                "value": ev, "unit": UNIT, "device": torch.cuda.get_device_name(dev),
+                "sample": f"oracle/ref_port.py (the reference's ATen operators in its order) as PyTorch CUDA eager on this GPU: "
+                          f"{B} windows x {ns_e} samples x {N - 1} steps in {edt:.2f} s, scaled to {G} samples/window",
+                "speedup_e2e": round(e2e_value / ev, 1)}
+        except Exception as exc:  # a reported baseline must never take the bench line down
+            cpu_baseline["reference_cuda_eager"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
