@@ -148,6 +148,10 @@ class MoCoDAD(_Base):
         self.anomaly_score_filter_kernel_size = args.filter_kernel_size
         self.anomaly_score_frames_shift = args.frames_shift
         self.dataset_name = args.dataset_choice
+        # where the trajectories live and their video resolution: only the device-ingest entry points read them
+        # (the reference hands them to get_dataset_and_loader, utils/dataset.py:270-331)
+        self.data_dir = getattr(args, "data_dir", None)
+        self.vid_res = getattr(args, "vid_res", None)
         # knobs new to this implementation (optional)
         self.rng_mode = getattr(args, "b200_rng", "philox")
         if self.rng_mode not in ("philox", "torch"):
@@ -393,7 +397,7 @@ class MoCoDAD(_Base):
         print(f'AUC score: {auc_score:.6f}')
         return auc_score
 
-    def score_trajectories(self, data_dir: str, vid_res, split: str = None, batch: int = 1024):
+    def score_trajectories(self, data_dir: str = None, vid_res=None, split: str = None, batch: int = 1024):
         """The test epoch straight from the reference's on-disk trajectories, bypassing the host
         dataset: what ``get_dataset_and_loader`` (utils/dataset.py:270-331 -> PoseDatasetRobust) + ``trainer.test`` produce,
         with the frame rows uploaded once and every dataset item built in HBM (``ScoringEngine.score_trajectories_host``).
@@ -407,6 +411,10 @@ class MoCoDAD(_Base):
             raise NotImplementedError("score_trajectories returns the 'best' aggregation (every shipped test config); use "
                                       "forward() on batches for the other strategies")
         split = self.split if split is None else split
+        data_dir = self.data_dir if data_dir is None else data_dir
+        vid_res = self.vid_res if vid_res is None else vid_res
+        if data_dir is None or vid_res is None or len(vid_res) != 2:
+            raise ValueError("score_trajectories needs data_dir and vid_res = [width, height] (arguments or YAML keys)")
         ts = ingest.load_trajectories(os.path.join(data_dir, ingest.split_subfolder(split), 'trajectories'))
         starts, meta, frames = ingest.window_table(ts, self.n_frames, 1)       # no strides for the test set (dataset.py:308)
         center, scale = ingest.load_robust_scaler(self.ckpt_dir)
@@ -420,7 +428,7 @@ class MoCoDAD(_Base):
         trans = np.repeat(np.arange(K, dtype=np.int64), N)                     # item idx -> idx // N (dataset.py:70-72)
         return scores, trans, np.tile(meta, (K, 1)), np.tile(frames, (K, 1))
 
-    def test_on_trajectories(self, data_dir: str, vid_res, split: str = None, batch: int = 1024) -> float:
+    def test_on_trajectories(self, data_dir: str = None, vid_res=None, split: str = None, batch: int = 1024) -> float:
         """``score_trajectories`` -> ``post_processing`` -> AUC: the device-ingest twin of eval_MoCoDAD.py:30-38."""
         scores, trans, meta, frames = self.score_trajectories(data_dir, vid_res, split=split, batch=batch)
         auc_score = self.post_processing(scores, None, trans, meta, frames)

@@ -69,3 +69,14 @@ def test_forward_refuses_to_run_without_cuda():
         pytest.skip("CUDA present")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.forward(batch)
+
+
+def test_trajectory_entry_points_validate_before_touching_the_gpu(tmp_path):
+    with pytest.raises(NotImplementedError):
+        make(aggregation_strategy="mean").score_trajectories(str(tmp_path), [640, 360])
+    with pytest.raises(ValueError, match="data_dir and vid_res"):
+        make().score_trajectories()
+    m = make(data_dir=str(tmp_path), vid_res=[640, 360])          # the YAML keys the reference passes to its dataset
+    assert m.data_dir == str(tmp_path) and m.vid_res == [640, 360]
+    with pytest.raises(FileNotFoundError):
+        m.score_trajectories()                                     # no {data_dir}/testing/trajectories
