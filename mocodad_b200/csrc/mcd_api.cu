@@ -286,8 +286,10 @@ int enc_block_op(int action, int idx, const mcd_model* m, const BlockWeights* w,
   return fail(MCD_ERR_INVALID_ARG, "bad encoder block index %d", idx);
 }
 
-// The frame counts this build carries kernels for.  Extend here (and only here).
-#define MCD_FOR_EACH_T(X) X(3) X(24)
+// The frame counts this build carries kernels for.  Extend here (and only here).  The tensor-core block kernel tiles
+// nw_for(T, 17) * T * V rows per CTA and needs whole 8-row swizzle atoms at every V of the joint pyramid (17 is odd), i.e.
+// windows-per-tile * T = 24: T in {3, 6, 12, 24} (seg_len 6 / 9 / 15 / 27 with three conditioning frames).
+#define MCD_FOR_EACH_T(X) X(3) X(6) X(12) X(24)
 #define MCD_FOR_EACH_TC(X) X(3)
 
 int unet_block_dispatch(int action, int T, int idx, const mcd_model* m, const BlockWeights* w, const BlockIO* io,

@@ -154,7 +154,7 @@ struct BlockCfg {
   static constexpr int NPG = kThreads / NCG;
   static constexpr int TPR = (ROWS + NPG - 1) / NPG;
   // T-mix tile: 4 channels x TQ output frames;  A-mix tile: 4 channels x TW output joints
-  static constexpr int TQ = TP4 <= 8 ? TP4 : 8;
+  static constexpr int TQ = TP4 <= 8 ? TP4 : (TP4 % 8 == 0 ? 8 : 4);
   static constexpr int NQT = TP4 / TQ;
   static constexpr int NWT = 2;
   static constexpr int TW = VP / NWT;

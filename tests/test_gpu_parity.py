@@ -333,3 +333,43 @@ def test_auc_parity_through_post_processing():
     phil = eng.reverse_diffusion(data.to(DEV), G, seed=999)["best"].cpu()
     auc_phil = postproc.dataset_auc(phil.numpy(), trans, meta, frames, gt, **kw)
     assert abs(auc_phil - auc_ref) <= 0.03, (auc_phil, auc_ref)
+
+
+EXTRA_T = [6, 12]   # further frame counts the library carries kernels for (MCD_FOR_EACH_T); no reference fixture: oracle on the fly
+
+
+@pytest.mark.parametrize("T", EXTRA_T)
+def test_every_layer_tap_other_frame_counts_vs_oracle(T):
+    seg_len, N, B = T + 3, 10, 5
+    eng, sd = _engine(seg_len, N)
+    batch = synth.synth_batch(B, seg_len, seed=21)
+    x0 = synth.synth_noise(1, N, B, T, seed=22)[0, 0]
+    with torch.no_grad():
+        cond, _ = ref_port.select_frames(batch[0], (0, 1, 2))
+        emb = ref_port.cond_encode(sd, cond)
+        taps = {}
+        eps = ref_port.unet_forward(sd, x0, torch.full((B,), 7, dtype=torch.long), emb, taps=taps)
+    np.testing.assert_allclose(_np(eng.cond_encode(batch[0].to(DEV))), emb.numpy(), rtol=0, atol=2e-5)
+    x = x0.to(DEV).contiguous()
+    for k, want in taps.items():
+        got = eng.unet_tap(x, 7, emb.to(DEV), k, want.shape[1], want.shape[3])
+        np.testing.assert_allclose(_np(got), want.numpy(), rtol=0, atol=2e-5, err_msg=f"T={T} {k}")
+    got = eng.unet_forward(x, 7, emb.to(DEV))
+    np.testing.assert_allclose(_np(got), eps.numpy(), rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("T", EXTRA_T)
+def test_reverse_diffusion_other_frame_counts_vs_oracle(T):
+    seg_len, N, G, B = T + 3, 10, 2, 37
+    eng, sd = _engine(seg_len, N)
+    batch = synth.synth_batch(B, seg_len, seed=31)
+    noise = synth.synth_noise(G, N, B, T, seed=32)
+    with torch.no_grad():
+        want, _ = ref_port.reverse_diffusion(sd, batch[0], noise_steps=N, n_generated_samples=G, noise=noise)
+    res = eng.reverse_diffusion(batch[0].to(DEV), G, noise=noise.to(DEV))
+    np.testing.assert_allclose(_np(res["best"]), want.numpy(), rtol=0, atol=1e-4)
+    # Philox mode: keyed by the global window index, invariant to how the batch is cut
+    whole = eng.reverse_diffusion(batch[0].to(DEV), G, seed=5)["best"]
+    parts = torch.cat([eng.reverse_diffusion(batch[0][a:b].to(DEV).contiguous(), G, seed=5, first_window=a)["best"]
+                       for a, b in ((0, 11), (11, 37))])
+    assert torch.equal(whole, parts)
