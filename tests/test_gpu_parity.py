@@ -17,7 +17,8 @@ from oracle import ref_port, synth
 
 pytestmark = pytest.mark.gpu
 
-CASES = {"avenue_T3": (6, 10, 3, 6), "plumb_N2": (6, 2, 2, 5), "stress_T24": (27, 10, 2, 3)}
+CASES = {"avenue_T3": (6, 10, 3, 6), "plumb_N2": (6, 2, 2, 5), "stress_T24": (27, 10, 2, 3),
+         "mid_T6": (9, 10, 2, 3), "mid_T12": (15, 10, 2, 3)}
 DEV = "cuda:0"
 
 
