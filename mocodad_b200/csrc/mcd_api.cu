@@ -290,7 +290,7 @@ int enc_block_op(int action, int idx, const mcd_model* m, const BlockWeights* w,
 // nw_for(T, 17) * T * V rows per CTA and needs whole 8-row swizzle atoms at every V of the joint pyramid (17 is odd), i.e.
 // windows-per-tile * T = 24: T in {3, 6, 12, 24} (seg_len 6 / 9 / 15 / 27 with three conditioning frames).
 #define MCD_FOR_EACH_T(X) X(3) X(6) X(12) X(24)
-#define MCD_FOR_EACH_TC(X) X(3)
+#define MCD_FOR_EACH_TC(X) X(3) X(6) X(12)  // conditioning frames: the shipped 3, and seg_len / 2 of the integer form (mocodad.py:708-741)
 
 int unet_block_dispatch(int action, int T, int idx, const mcd_model* m, const BlockWeights* w, const BlockIO* io,
                         cudaStream_t s) {

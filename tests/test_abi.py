@@ -63,6 +63,7 @@ def test_shape_support_table(lib):
     assert lib.mcd_shape_supported(24, 3) == 1
     assert lib.mcd_shape_supported(3, 0) == 1
     assert lib.mcd_shape_supported(6, 3) == 1 and lib.mcd_shape_supported(12, 3) == 1
+    assert lib.mcd_shape_supported(6, 6) == 1 and lib.mcd_shape_supported(12, 12) == 1 and lib.mcd_shape_supported(3, 4) == 0
     assert lib.mcd_shape_supported(5, 3) == 0 and lib.mcd_shape_supported(9, 3) == 0
 
 

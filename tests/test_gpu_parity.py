@@ -173,7 +173,8 @@ def test_loss_functions_vs_oracle(loss_fn):
     np.testing.assert_allclose(_np(res["worst"]), want.max(0)[0].numpy(), rtol=2e-6, atol=1e-6)
 
 
-@pytest.mark.parametrize("seg_len,n_cond,cond_first", [(6, 3, False), (3, 0, True), (24, 0, True)])
+@pytest.mark.parametrize("seg_len,n_cond,cond_first", [(6, 3, False), (3, 0, True), (24, 0, True), (12, 6, True), (24, 12, True),
+                                                        (12, 6, False)])
 def test_other_conditioning_layouts_vs_oracle(seg_len, n_cond, cond_first):
     """Conditioning on the LAST frames, and 'no_condition' (whole window denoised, no encoder)."""
     N, G, B = 4, 2, 5
