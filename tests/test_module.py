@@ -80,3 +80,26 @@ def test_trajectory_entry_points_validate_before_touching_the_gpu(tmp_path):
     assert m.data_dir == str(tmp_path) and m.vid_res == [640, 360]
     with pytest.raises(FileNotFoundError):
         m.score_trajectories()                                     # no {data_dir}/testing/trajectories
+
+
+def test_product_package_never_touches_the_oracle_or_a_cpu_path():
+    """The oracle is test infrastructure: nothing under mocodad_b200/ may import it, and the CUDA library is the only
+    implementation (a missing library or a CPU device is an error, never a fallback)."""
+    import ast
+    import os
+    import mocodad_b200
+    pkg = os.path.dirname(mocodad_b200.__file__)
+    for fn in sorted(os.listdir(pkg)):
+        if not fn.endswith(".py"):
+            continue
+        tree = ast.parse(open(os.path.join(pkg, fn)).read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            assert not any(n == "oracle" or n.startswith("oracle.") for n in names), f"{fn} imports the oracle"
+    from mocodad_b200 import ScoringEngine
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ScoringEngine(seg_len=6, n_frames_cond=3, noise_steps=10, device="cpu")
