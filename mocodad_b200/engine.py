@@ -307,6 +307,19 @@ class ScoringEngine:
                                            int(first_item), n_items, out.data_ptr(), self._stream()))
         return out
 
+    def fit_scaler_host(self, coords: np.ndarray, lengths: np.ndarray, vid_res: Sequence[float], *, seg_stride: int = 1,
+                        exp_dir: Optional[str] = None):
+        """Train-split scaler fit (utils/get_robust_data.py:115-119): the frame rows are normalised on the device
+        (``normalize_frames`` without a scaler), the quantiles are sklearn's own ``RobustScaler.fit`` on the host
+        (``mocodad_b200.ingest.fit_robust_scaler``); with ``exp_dir`` the estimator is pickled where the test split looks for it."""
+        from . import ingest
+        coords = np.ascontiguousarray(coords, dtype=np.float32)
+        if coords.ndim != 2 or coords.shape[1] != 2 * N_JOINTS:
+            raise ValueError(f"coords: expected [F,{2 * N_JOINTS}], got {coords.shape}")
+        d_rows = torch.from_numpy(coords).to(self.device)
+        norm = self.normalize_frames(d_rows, vid_res, out=d_rows).cpu().numpy()
+        return ingest.fit_robust_scaler(norm, lengths, self.seg_len, seg_stride, exp_dir=exp_dir)
+
     def score_trajectories_host(self, coords: np.ndarray, win_start: np.ndarray, center: np.ndarray, scale: np.ndarray,
                                 vid_res: Sequence[float], n_generated_samples: int, *, num_transform: int = 5, batch: int = 1024,
                                 seed: int = 0, row_step: int = 1, item_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:

@@ -11,6 +11,7 @@ Host-side pieces (this file) and the reference code they stand for:
   load_trajectories   utils/data.py:233-251  (folders ``{scene}-{clip}``, files ``{person}.csv``, rows ``frame,x1,y1,...,x17,y17``)
   window_table        utils/preprocessing.py:4-10, 14-52, 55-86  (window starts, [scene, clip, person, first frame] meta, frame ids)
   load_robust_scaler  utils/get_robust_data.py:18-22, 115-127  (``{exp_dir}/local_robust.pickle`` must exist for the test split)
+  fit_robust_scaler   utils/get_robust_data.py:115-119, utils/data.py:345-349  (train split: fit + pickle, on device-normalised rows)
 The arithmetic itself lives in csrc/mcd_kernels.cuh; there is no host implementation of it in this package.
 """
 from __future__ import annotations
@@ -110,3 +111,29 @@ def scaler_arrays(scaler) -> Tuple[np.ndarray, np.ndarray]:
     if center.shape != (ROW,) or scale.shape != (ROW,):
         raise ValueError(f"robust scaler must be fitted with centering and scaling on {ROW} columns")
     return center, scale
+
+
+def fit_robust_scaler(norm_rows: np.ndarray, lengths: np.ndarray, seg_len: int, seg_stride: int = 1, exp_dir: str = None,
+                      strategy: str = "robust"):
+    """The train-split half of the scaler handling (get_robust_data.py:115-119 -> scale_trajectories_robust, utils/data.py:345-349):
+    fit sklearn's ``RobustScaler(quantile_range=(10, 90))`` -- the reference's own estimator, like ``roc_auc_score`` in the AUC
+    tail -- on the bounding-box-centre rows of every trajectory long enough to yield a window (``remove_short_trajectories``
+    runs first, preprocessing.py:4-10), zeros counted as missing.  ``norm_rows`` [F,34] are the rows ``mcd_normalize_frames``
+    produced WITHOUT a scaler, back to back like ``TrajectorySet.coords``.  With ``exp_dir`` the estimator is pickled as
+    ``local_{strategy}.pickle``, the file the test split loads.  Returns the fitted estimator."""
+    from sklearn.preprocessing import RobustScaler
+    norm_rows = np.asarray(norm_rows, dtype=np.float32)
+    lengths = np.asarray(lengths, dtype=np.int64)
+    if norm_rows.shape != (int(lengths.sum()), ROW):
+        raise ValueError(f"norm_rows: expected [{int(lengths.sum())},{ROW}], got {norm_rows.shape}")
+    span = seg_len + (seg_stride - 1) * (seg_len - 1)
+    keep = np.repeat(lengths >= span, lengths)
+    X = norm_rows[keep]
+    if X.shape[0] == 0:
+        raise ValueError("fit_robust_scaler: no trajectory is long enough for one window")
+    scaler = RobustScaler(quantile_range=(10.0, 90.0))
+    scaler.fit(np.where(X == 0.0, np.nan, X))
+    if exp_dir is not None:
+        with open(os.path.join(exp_dir, f"local_{strategy}.pickle"), "wb") as fh:
+            pickle.dump(scaler, fh)
+    return scaler

@@ -97,6 +97,13 @@ def main():
         with open(os.path.join(exp_dir, "local_robust.pickle"), "rb") as fh:
             sk = pickle.load(fh)
         print("scaler attribute dtypes:", sk.center_.dtype, sk.scale_.dtype)
+        # the train-split fit restated: rows of the training tree -> oracle normalisation -> ingest.fit_robust_scaler
+        tr = ingest.load_trajectories(os.path.join(root, "training", "trajectories"))
+        fitted = ingest.fit_robust_scaler(otr.bbox_centre_normalize(tr.coords, VID_RES), tr.lengths, 6, 1)
+        assert fitted.center_.dtype == sk.center_.dtype and fitted.center_.tobytes() == sk.center_.tobytes(), "center_ differs"
+        assert fitted.scale_.dtype == sk.scale_.dtype and fitted.scale_.tobytes() == sk.scale_.tobytes(), "scale_ differs"
+        print("RobustScaler fit on", len(tr), "training trajectories: bit-identical to the reference's pickle")
+        out.update(train_coords=tr.coords, train_lengths=tr.lengths)
         ts = ingest.load_trajectories(os.path.join(root, "testing", "trajectories"))
         out.update(coords=ts.coords, frames=ts.frames, lengths=ts.lengths, ids=ts.ids, center=center, scale=scale,
                    vid_res=np.asarray(VID_RES, dtype=np.float32))

@@ -74,6 +74,22 @@ def test_bbox_normalisation_properties():
     assert np.all(out[~g["coords"].any(axis=1)] == 0)            # missing frames too
 
 
+def test_scaler_fit_matches_the_reference_pickle(tmp_path):
+    """Train split: RobustScaler fitted on the normalised training rows == the estimator the reference pickled."""
+    g = np.load(GOLD)
+    rows = otr.bbox_centre_normalize(g["train_coords"], g["vid_res"])
+    sk = ingest.fit_robust_scaler(rows, g["train_lengths"], 6, 1, exp_dir=str(tmp_path))
+    assert sk.center_.dtype == np.float32 and np.array_equal(sk.center_.astype(np.float64), g["center"])
+    assert np.array_equal(np.asarray(sk.scale_, dtype=np.float64), g["scale"])
+    center, scale = ingest.load_robust_scaler(str(tmp_path))          # the pickle the test split loads
+    assert np.array_equal(center, g["center"]) and np.array_equal(scale, g["scale"])
+    assert (g["train_lengths"] < 6).any()                              # the short trajectory is excluded like upstream
+    with pytest.raises(ValueError):
+        ingest.fit_robust_scaler(rows[:-1], g["train_lengths"], 6)
+    with pytest.raises(ValueError):
+        ingest.fit_robust_scaler(rows, g["train_lengths"], 1000)
+
+
 def _engine(seg_len):
     from mocodad_b200 import ScoringEngine, synthetic as synth
     eng = ScoringEngine(seg_len=seg_len, n_frames_cond=3, noise_steps=4, device="cuda:0")
@@ -205,3 +221,11 @@ def test_module_scores_a_trajectory_tree_like_the_batch_path(tmp_path):
     auc_batches = model.on_test_epoch_end()
     auc = model.test_on_trajectories(str(data_dir), g["vid_res"], batch=77)
     assert 0.0 <= auc <= 1.0 and auc == auc_batches
+
+
+@pytest.mark.gpu
+def test_scaler_fit_on_device_normalised_rows_matches_the_reference_pickle():
+    g = np.load(GOLD)
+    eng = _engine(6)
+    sk = eng.fit_scaler_host(g["train_coords"], g["train_lengths"], g["vid_res"])
+    assert np.array_equal(sk.center_.astype(np.float64), g["center"]) and np.array_equal(np.asarray(sk.scale_, np.float64), g["scale"])
