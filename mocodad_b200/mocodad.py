@@ -428,6 +428,17 @@ class MoCoDAD(_Base):
         trans = np.repeat(np.arange(K, dtype=np.int64), N)                     # item idx -> idx // N (dataset.py:70-72)
         return scores, trans, np.tile(meta, (K, 1)), np.tile(frames, (K, 1))
 
+    def fit_trajectory_scaler(self, data_dir: str = None, vid_res=None, split: str = 'train'):
+        """The train split's scaler step (utils/get_robust_data.py:115-119): fit the RobustScaler on the training trajectories
+        (rows normalised on the device) and pickle it as ``{ckpt_dir}/local_robust.pickle`` for ``score_trajectories``."""
+        from . import ingest
+        data_dir = self.data_dir if data_dir is None else data_dir
+        vid_res = self.vid_res if vid_res is None else vid_res
+        if data_dir is None or vid_res is None or len(vid_res) != 2:
+            raise ValueError("fit_trajectory_scaler needs data_dir and vid_res = [width, height] (arguments or YAML keys)")
+        ts = ingest.load_trajectories(os.path.join(data_dir, ingest.split_subfolder(split), 'trajectories'))
+        return self.engine().fit_scaler_host(ts.coords, ts.lengths, vid_res, exp_dir=self.ckpt_dir)
+
     def test_on_trajectories(self, data_dir: str = None, vid_res=None, split: str = None, batch: int = 1024) -> float:
         """``score_trajectories`` -> ``post_processing`` -> AUC: the device-ingest twin of eval_MoCoDAD.py:30-38."""
         scores, trans, meta, frames = self.score_trajectories(data_dir, vid_res, split=split, batch=batch)

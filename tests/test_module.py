@@ -103,3 +103,10 @@ def test_product_package_never_touches_the_oracle_or_a_cpu_path():
     from mocodad_b200 import ScoringEngine
     with pytest.raises(RuntimeError, match="no CPU path"):
         ScoringEngine(seg_len=6, n_frames_cond=3, noise_steps=10, device="cpu")
+
+
+def test_fit_trajectory_scaler_validates_its_inputs(tmp_path):
+    with pytest.raises(ValueError, match="data_dir and vid_res"):
+        make().fit_trajectory_scaler()
+    with pytest.raises(FileNotFoundError):
+        make(data_dir=str(tmp_path), vid_res=[640, 360]).fit_trajectory_scaler()   # no {data_dir}/training/trajectories
