@@ -17,4 +17,7 @@ def __getattr__(name):  # lazy: keep `import mocodad_b200` cheap and torch-free 
     if name == "MoCoDAD":
         from .mocodad import MoCoDAD
         return MoCoDAD
+    if name == "MoCoDADlatent":   # name kept for eval_MoCoDAD.py:24; raises NotImplementedError
+        from .mocodad import MoCoDADlatent
+        return MoCoDADlatent
     raise AttributeError(name)

@@ -479,3 +479,15 @@ def _processing_data(data):
         for c, t in zip(cols, arr[:5]):
             c.append(t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t))
     return tuple(np.concatenate(c, axis=0) for c in cols)
+
+
+class MoCoDADlatent(MoCoDAD):
+    """Name kept for ``eval_MoCoDAD.py:24`` (``MoCoDADlatent(args) if hasattr(args, 'diffusion_on_latent')``).  The latent
+    variant (models/mocodad_latent.py: one STSE_Unet encoder pass per batch, then an MLP denoiser over [B, latent] vectors) has
+    no CUDA path yet; its oracle is pinned (oracle/latent_port.py, tests/golden/latent_T3.npz).
+    Constructing it fails loudly instead of scoring with the wrong model."""
+
+    def __init__(self, args: argparse.Namespace) -> None:
+        raise NotImplementedError("MoCoDADlatent (diffusion on the latent space) is outside the B200 scoring path so far "
+                                  "(SURVEY.md section 8 row f4); use the reference for 'diffusion_on_latent' configs")
+
