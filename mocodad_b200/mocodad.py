@@ -418,7 +418,10 @@ class MoCoDAD(_Base):
         ts = ingest.load_trajectories(os.path.join(data_dir, ingest.split_subfolder(split), 'trajectories'))
         starts, meta, frames = ingest.window_table(ts, self.n_frames, 1)       # no strides for the test set (dataset.py:308)
         center, scale = ingest.load_robust_scaler(self.ckpt_dir)
-        K, N = max(int(self.num_transforms), 1), len(starts)
+        if int(self.num_transforms) < 1:
+            raise NotImplementedError("num_transform < 1: the reference's untransformed dataset path applies a random temporal crop "
+                                      "per item (utils/dataset.py:77-83, 127-130), which has no device counterpart")
+        K, N = int(self.num_transforms), len(starts)
         total = K * N
         rank, world = (dist.get_rank(), dist.get_world_size()) if (dist.is_available() and dist.is_initialized()) else (0, 1)
         lo, hi = sharding.shard_bounds(total, rank, world)
