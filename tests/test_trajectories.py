@@ -229,3 +229,24 @@ def test_scaler_fit_on_device_normalised_rows_matches_the_reference_pickle():
     eng = _engine(6)
     sk = eng.fit_scaler_host(g["train_coords"], g["train_lengths"], g["vid_res"])
     assert np.array_equal(sk.center_.astype(np.float64), g["center"]) and np.array_equal(np.asarray(sk.scale_, np.float64), g["scale"])
+
+
+def test_window_table_equals_the_loop_restatement_on_random_trajectory_sets():
+    """Vectorised host table (mocodad_b200/ingest.py) vs the loop restatement of preprocessing.py:55-86, ragged inputs."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(lengths=st.lists(st.integers(min_value=0, max_value=40), min_size=0, max_size=8),
+           seg_len=st.integers(min_value=1, max_value=12), stride=st.integers(min_value=1, max_value=3), seed=st.integers(0, 2**16))
+    def check(lengths, seg_len, stride, seed):
+        rng = np.random.default_rng(seed)
+        F = int(sum(lengths))
+        frames = (np.cumsum(rng.integers(1, 3, size=F)) if F else np.zeros(0)).astype(np.int32)
+        ids = rng.integers(0, 50, size=(len(lengths), 3)).astype(np.int64)
+        ts = ingest.TrajectorySet(np.zeros((F, 34), np.float32), frames, np.asarray(lengths, dtype=np.int64), ids, [])
+        s, m, f = ingest.window_table(ts, seg_len, stride)
+        os_, om, of = otr.window_table(ts.lengths, ts.frames, ts.ids, seg_len, stride)
+        assert s.dtype == np.int64 and np.array_equal(s, os_) and np.array_equal(m, om) and np.array_equal(f, of)
+        if len(s):
+            assert s.max() + (seg_len - 1) * stride < F and (np.diff(s) > 0).all()
+    check()
