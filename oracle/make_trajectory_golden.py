@@ -76,11 +76,11 @@ def check_stress_rows():
     """oracle == reference on the random sweep the GPU test uses (utils/data.py:165-187 called directly)."""
     from utils.data import Trajectory
     rows = otr.stress_rows(11)
-    for res in ([640, 360], [1080, 720]):
+    for res in ([640, 360], [856, 480], [1080, 720]):   # the three shipped video resolutions (config/*/mocodad_test.yaml: vid_res)
         ref = Trajectory._from_image_to_centre_bounding_box(rows.copy(), video_resolution=np.array(res, dtype=np.float32))
         got = otr.bbox_centre_normalize(rows, res)
         assert ref.dtype == got.dtype and ref.tobytes() == got.tobytes(), (res, np.abs(ref - got).max())
-    print("bbox-centre normalisation: oracle bit-identical to the reference on", 2 * len(rows), "stress rows")
+    print("bbox-centre normalisation: oracle bit-identical to the reference on", 3 * len(rows), "stress rows")
 
 
 def main():
