@@ -8,3 +8,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 # one denoiser call = time_embedding + 11 blocks + 4 resamples + ddpm = 17 launches; skip the encoder (5), randn (1) and the first call
 timeout 900 ncu --set full --clock-control none --import-source on --launch-skip 23 -c 17 -f -o gpurun_out/${tag}_full $CMD > gpurun_out/${tag}_full.log 2>&1; echo "full rc=$?"
 ls -la gpurun_out | grep ${tag}
+# (3) the window-ingest kernels: plain timing first (CUDA events, never under ncu), then ncu --set full
+timeout 300 python tools/ingest_profile.py --time > gpurun_out/${tag}_ingest_time.log 2>&1; tail -2 gpurun_out/${tag}_ingest_time.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'normalize_frames|build_items' -c 4 -f -o gpurun_out/${tag}_ingest \
+  python tools/ingest_profile.py > gpurun_out/${tag}_ingest.log 2>&1; echo "ingest rc=$?"
