@@ -45,6 +45,7 @@ def parse_args():
     p.add_argument("--eager-samples", type=int, default=5, help="generated samples timed by the PyTorch CUDA-eager baseline arm")
     p.add_argument("--ref-sample", default="32x5", help="--impl reference: windows x samples per step")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-shipped", action="store_true", help="skip the shipped-shape (T=3, B=1024 / 2048) sub-record")
     return p.parse_args()
 
 
@@ -56,7 +57,7 @@ def workload_config(a):
             "windows_per_gpu_per_step": a.batch, "seg_len": a.seg_len, "T": T, "V": 17,
             "noise_steps": a.noise_steps, "n_generated_samples": a.gen,
             "window_steps_per_window": a.gen * (a.noise_steps - 1),
-            "cache": "per-step working set (activations of a 17168-window pass, ~6.5 GB) exceeds the 126 MB L2; "
+            "cache": "per-step working set (activations of one pass of the virtual batch, GBs) exceeds the 126 MB L2; "
                      "fresh Philox noise every step"}
 
 
@@ -188,11 +189,30 @@ def run_reference(a):
 
 
 # --------------------------------------------------------------------------- CUDA arm
+def _stdout_to_stderr():
+    """NCCL prints its INFO lines (the communicator / rank lines the driver checks) on the process's stdout.  Route fd 1 to
+    stderr so they stay visible, and hand back a private copy of the original stdout for the one JSON line."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _emit(fd, line: dict):
+    text = json.dumps(line) + "\n"
+    if fd is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(fd, text.encode())
+
+
 def run_b200(a):
     import torch.distributed as dist
     from mocodad_b200 import ScoringEngine
     from mocodad_b200.engine import probe_fp32_detail
     from mocodad_b200 import synthetic as synth
+    from mocodad_b200.sharding import gather_scores
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -202,10 +222,12 @@ def run_b200(a):
                          "for the host-core baseline)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    out_fd = None
     if world > 1:
-        # keep stdout to the single JSON line: NCCL's version banner goes to stdout at INFO/VERSION level
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO") and not os.environ.get("MCD_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL's communicator lines must reach the driver (it checks the rank count); they go to stderr, the JSON line alone to stdout
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        out_fd = _stdout_to_stderr()
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -220,58 +242,69 @@ def run_b200(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    T = a.seg_len - 3
-    B, G, N = a.batch, a.gen, a.noise_steps
-    eng = ScoringEngine(seg_len=a.seg_len, n_frames_cond=3, noise_steps=N, device=dev)
-    eng.load_state_dict(synth.synth_state_dict(synth.state_dict_spec(T=T, T_cond=3), seed=0))
-    host = synth.synth_batch(B, a.seg_len, seed=1 + rank)[0].pin_memory()
-    data = host.to(dev)
-    first = rank * B  # this rank's windows in the global index space (weak scaling: B windows per rank)
-    step_no = [0]
+    G, N = a.gen, a.noise_steps
 
-    from mocodad_b200.sharding import gather_scores
+    def measure(seg_len: int, B: int, steps: int, warmup: int, sample_clocks: bool):
+        """value (inputs resident in HBM, device-timed) and e2e (host buffers through mcd_score_windows_host) for one shape."""
+        T = seg_len - 3
+        eng = ScoringEngine(seg_len=seg_len, n_frames_cond=3, noise_steps=N, device=dev)
+        eng.load_state_dict(synth.synth_state_dict(synth.state_dict_spec(T=T, T_cond=3), seed=0))
+        host = synth.synth_batch(B, seg_len, seed=1 + rank)[0].pin_memory()
+        data = host.to(dev)
+        first = rank * B  # this rank's windows in the global index space (weak scaling: B windows per rank)
+        step_no = [0]
 
-    def step_device():
-        res = eng.reverse_diffusion(data, G, seed=999, first_window=first + step_no[0] * world * B)
-        step_no[0] += 1
-        # N > 1: the path's one exchange -- all-gather of the per-window scores
-        return gather_scores(res["best"], world * B) if world > 1 else res["best"]
+        def step_device():
+            res = eng.reverse_diffusion(data, G, seed=999, first_window=first + step_no[0] * world * B)
+            step_no[0] += 1
+            # N > 1: the path's one exchange -- all-gather of the per-window scores (SURVEY.md 8e)
+            return gather_scores(res["best"], world * B) if world > 1 else res["best"]
 
-    def step_host():
-        out = eng.score_windows_host(host, G, seed=999, first_window=first + step_no[0] * world * B)
-        step_no[0] += 1
-        return out
+        def step_host():
+            out = eng.score_windows_host(host, G, seed=999, first_window=first + step_no[0] * world * B)
+            step_no[0] += 1
+            if world > 1:   # the same exchange, end to end: scores back onto the device, one all-gather, all scores to the host
+                out = gather_scores(out.to(dev, non_blocking=True), world * B).cpu()
+            return out
 
-    # ---- value: inputs resident in HBM, device-timed --------------------------------------
-    for _ in range(a.warmup):
-        step_device()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = eng.launch_count()
-    with ClockSampler(local) as clocks:
+        for _ in range(warmup):
+            step_device()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = eng.launch_count()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.__enter__()
         barrier()
         ev0.record()
-        for _ in range(a.steps):
+        for _ in range(steps):
             best = step_device()
         ev1.record()
         barrier()
-    launches = eng.launch_count() - launches0
-    ms = max_over_ranks(ev0.elapsed_time(ev1)) / a.steps
-    value = world * B / (ms * 1e-3)
-    assert bool(torch.isfinite(best).all())
+        if sampler:
+            sampler.__exit__()
+        launches = eng.launch_count() - launches0
+        ms = max_over_ranks(ev0.elapsed_time(ev1)) / steps
+        assert bool(torch.isfinite(best).all())
+        for _ in range(min(warmup, 2)):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            scores = step_host()
+        torch.cuda.synchronize(dev)
+        e2e_s = max_over_ranks(time.perf_counter() - t0) / steps
+        barrier()
+        assert bool(torch.isfinite(scores).all())
+        return {"eng": eng, "host": host, "data": data, "ms": ms, "value": world * B / (ms * 1e-3), "e2e_s": e2e_s,
+                "e2e_value": world * B / e2e_s, "launches": launches, "clocks": sampler.summary() if sampler else None,
+                "step_device": step_device}
 
-    # ---- e2e: host buffers through the C-ABI host entry (H2D + loop + D2H + sync per step) ----
-    for _ in range(min(a.warmup, 2)):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        scores = step_host()
-    torch.cuda.synchronize(dev)
-    e2e_s = max_over_ranks(time.perf_counter() - t0) / a.steps
-    barrier()
-    e2e_value = world * B / e2e_s
-    assert bool(torch.isfinite(scores).all())
+    T = a.seg_len - 3
+    B = a.batch
+    main = measure(a.seg_len, B, a.steps, a.warmup, True)
+    eng, host, data, ms, value, e2e_s, e2e_value = (main[k] for k in ("eng", "host", "data", "ms", "value", "e2e_s", "e2e_value"))
+    launches, clocks_summary, step_device = main["launches"], main["clocks"], main["step_device"]
 
     # ---- row f1: dataset items (5 affine transforms per base window) built on the device ----------
     from mocodad_b200.engine import pose_transform_matrices
@@ -346,55 +379,81 @@ def run_b200(a):
     top = kernels[0]
     pv = prof[top["kernel"]]
 
+    # ---- the shipped shape (every config under config/ has seg_len 6 -> T = 3; batch 1024 Avenue / UBnormal, 2048 STC) ----
+    shipped = None
+    if not a.no_shipped and a.seg_len != 6:
+        shipped = []
+        for sb in (1024, 2048):
+            r = measure(6, sb, max(3, a.steps), 3, False)
+            algo = 230952.0 * G * (N - 1)   # algorithmic bytes per window (per-block-fused contract, T=3)
+            shipped.append({"r": r, "B": sb, "algo": algo})
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        hbm_peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+    if "hbm_gbs" in peaks:
+        hbm_peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
     else:
         hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     ffma_peak, ffma2_peak = probe_fp32_detail(local)
     fp32_peak = max(ffma_peak, ffma2_peak)
     top_sec_per_launch = pv["ms"] * 1e-3 / pv["launches"]
-    top_bytes_per_launch = pv["bytes_per_window"] * pv["windows"] / pv["launches"]
-    top_flops_per_launch = pv["flops_per_window"] * pv["windows"] / pv["launches"]
+    windows_per_launch = pv["windows"] / pv["launches"]
+    top_bytes_per_launch = pv["bytes_per_window"] * windows_per_launch
+    top_flops_per_launch = pv["flops_per_window"] * windows_per_launch
     achieved = top_bytes_per_launch / top_sec_per_launch / 1e9
     per_call = [k for k in prof if k.startswith("st_gcnn") or k in ("down1", "down2", "up3", "up2", "ddpm_step")]
     unet_flops = sum(prof[k]["flops_per_window"] for k in per_call)  # one denoiser call + DDPM update, per window
-    # measured DRAM traffic of that kernel (ncu --set full, profiles/r01_ncu_traffic.json), scaled to this launch size
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        per_window = tj["dram_bytes_per_window"].get(top["kernel"]) if tj.get("T", 24) == T else None  # captured at T=24
-        if per_window is not None:
-            traffic = per_window * pv["windows"] / pv["launches"]
+    unet_bytes = {3: 230952.0, 24: 1847616.0}.get(T)                 # algorithmic bytes per window-step
+    # measured DRAM traffic of that kernel: ncu --set full capture (profiles/ncu_traffic.json; per window at the launch size named there)
+    traffic, traffic_src = None, None
+    for tname in ("ncu_traffic.json", "r01_ncu_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            per_window = tj["dram_bytes_per_window"].get(top["kernel"]) if tj.get("T", 24) == T else None
+            if per_window is not None:
+                traffic = per_window * windows_per_launch
+                traffic_src = f"profiles/{tname} ({tj.get('windows_per_launch', 2368)} windows per captured launch)"
+                break
     # tensor-pipe view of the same kernel: 3xTF32 executes 3 tf32 MMAs per fp32 product of the 1x1 convolution(s)
-    peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
     tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
-    conv = {"st_gcnnsd1.1": (32, 32, 17), "st_gcnnsd2.0": (32, 64, 12), "st_gcnnsd2.1": (64, 64, 12), "st_gcnnsd3.0": (64, 128, 10),
-            "st_gcnnsd3.1": (128, 64, 10), "st_gcnnsu4.0": (64, 64, 12), "st_gcnnsu4.1": (64, 32, 12), "st_gcnnsu3.0": (32, 32, 17)}
+    conv = {"st_gcnnsd1.0": (16, 32, 17), "st_gcnnsd1.1": (32, 32, 17), "st_gcnnsd2.0": (32, 64, 12), "st_gcnnsd2.1": (64, 64, 12),
+            "st_gcnnsd3.0": (64, 128, 10), "st_gcnnsd3.1": (128, 64, 10), "st_gcnnsu4.0": (64, 64, 12), "st_gcnnsu4.1": (64, 32, 12),
+            "st_gcnnsu3.0": (32, 32, 17)}
     tensor = None
     if top["kernel"] in conv:
         ci, co, v = conv[top["kernel"]]
-        mma_flops = 3 * 2.0 * ci * co * T * v * (2 if ci != co else 1) * pv["windows"] / pv["launches"]
+        mma_flops = 3 * 2.0 * ci * co * T * v * (2 if ci != co else 1) * windows_per_launch
         tensor = {"achieved_tflops": round(mma_flops / top_sec_per_launch / 1e12, 1), "peak_tflops": round(tf32_peak, 1),
                   "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (kind::tf32 runs at half the bf16 rate)",
                   "frac": round(mma_flops / top_sec_per_launch / 1e12 / tf32_peak, 4),
                   "note": "tcgen05.mma kind::tf32, three MMAs per fp32 product (hi*hi + hi*lo + lo*hi)"}
-    roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src, "tensor": tensor,
-                "us_per_launch": round(top_sec_per_launch * 1e6, 1),
-                "algorithmic_bytes_per_launch": top_bytes_per_launch,
-                "note": "the dominant kernel is bound by the fp32 FMA pipe + shared memory (position mixes), with its channel contraction on the tensor pipe; HBM is not the limiter (SURVEY.md 8d): see 'fp32' and 'tensor'",
-                "fp32": {"achieved_tflops": round(top_flops_per_launch / top_sec_per_launch / 1e12, 2),
-                         "peak_tflops": round(fp32_peak, 2), "peak_source": "mcd_probe_fp32_detail: max of FFMA / FFMA2 register loops on this GPU",
-                         "probe_ffma_tflops": round(ffma_peak, 2), "probe_ffma2_tflops": round(ffma2_peak, 2),
-                         "frac": round(top_flops_per_launch / top_sec_per_launch / 1e12 / fp32_peak, 4),
-                         "whole_step_tflops": round(B * G * (N - 1) * unet_flops / (ms * 1e-3) / 1e12, 2)}}
+    fp32 = {"achieved_tflops": round(top_flops_per_launch / top_sec_per_launch / 1e12, 2),
+            "peak_tflops": round(fp32_peak, 2), "peak_source": "mcd_probe_fp32_detail: max of FFMA / FFMA2 register loops on this GPU",
+            "probe_ffma_tflops": round(ffma_peak, 2), "probe_ffma2_tflops": round(ffma2_peak, 2),
+            "frac": round(top_flops_per_launch / top_sec_per_launch / 1e12 / fp32_peak, 4),
+            "whole_step_tflops": round(B * G * (N - 1) * unet_flops / (ms * 1e-3) / 1e12, 2)}
+    hbm = {"achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4)}
+    # which roofline the dominant kernel sits closest to (largest fraction of its peak)
+    fracs = {"hbm": hbm["frac"], "fp32": fp32["frac"], "tensor": tensor["frac"] if tensor else 0.0}
+    bound = max(fracs, key=fracs.get)
+    head = {"hbm": (hbm["achieved"], hbm_peak, "GB/s"), "fp32": (fp32["achieved_tflops"], fp32["peak_tflops"], "TFLOP/s"),
+            "tensor": ((tensor or {}).get("achieved_tflops"), (tensor or {}).get("peak_tflops"), "TFLOP/s")}[bound]
+    roofline = {"bound": bound, "kernel": top["kernel"], "achieved": head[0], "peak": head[1], "unit": head[2],
+                "frac": fracs[bound], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "us_per_launch": round(top_sec_per_launch * 1e6, 1), "windows_per_launch": windows_per_launch,
+                "algorithmic_bytes_per_launch": top_bytes_per_launch, "hbm": hbm, "fp32": fp32, "tensor": tensor,
+                "note": "'bound' = the roofline of the dominant kernel with the largest achieved fraction (hbm: algorithmic activation bytes "
+                        "in + out; fp32: position mixes on the FMA pipe + convolution flops; tensor: 3xTF32 MMAs of the 1x1 convolutions)",
+                "whole_step_hbm": None if unet_bytes is None else {
+                    "achieved": round(B * G * (N - 1) * unet_bytes / (ms * 1e-3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
+                    "frac": round(B * G * (N - 1) * unet_bytes / (ms * 1e-3) / 1e9 / hbm_peak, 4),
+                    "note": "all kernels of a step: algorithmic bytes per window-step (SURVEY.md 8d) x window-steps / step time"}}
 
     cpu_baseline = None
     if world == 1 and not a.no_cpu_baseline:
@@ -411,18 +470,51 @@ def run_b200(a):
                 "sample": f"oracle/ref_port.py (the reference's ATen operators in its order) as PyTorch CUDA eager on this GPU: "
                           f"{B} windows x {ns_e} samples x {N - 1} steps in {edt:.2f} s, scaled to {G} samples/window",
                 "speedup_e2e": round(e2e_value / ev, 1)}
+            cpu_baseline["sample"] += (f" || PyTorch CUDA-eager arm (same operators on this {torch.cuda.get_device_name(dev)}, B={B}, {ns_e} of {G} "
+                                       f"samples timed): {ev:.1f} windows/s -> this path is {e2e_value / ev:.1f}x end to end")
         except Exception as exc:  # a reported baseline must never take the bench line down
             cpu_baseline["reference_cuda_eager"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
+    shipped_T3 = None
+    if shipped:
+        shipped_T3 = []
+        for rec in shipped:
+            r, sb = rec["r"], rec["B"]
+            entry = {"workload": f"synthetic windows [B,2,3,17] (seg_len 6, every shipped config), B={sb}/GPU, noise_steps={N}, "
+                                 f"n_generated_samples={G}", "windows_per_gpu_per_step": sb, "value": r["value"], "unit": UNIT,
+                     "ms_per_step": r["ms"], "window_steps_per_sec": r["value"] * G * (N - 1),
+                     "e2e": {"value": r["e2e_value"], "unit": UNIT, "ms_per_step": r["e2e_s"] * 1e3,
+                             "h2d_bytes_per_step": r["host"].numel() * 4, "d2h_bytes_per_step": sb * 4},
+                     "whole_step_hbm": {"achieved": round(rec["algo"] * r["value"] / world / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
+                                        "frac": round(rec["algo"] * r["value"] / world / 1e9 / hbm_peak, 4)},
+                     "gpu_launches": r["launches"]}
+            if world == 1 and not a.no_cpu_baseline:
+                try:
+                    a3 = argparse.Namespace(**dict(vars(a), seg_len=6, batch=sb))
+                    ev3, edt3 = cuda_eager_reference_rate(a3, dev, max(1, min(G, a.eager_samples)))
+                    entry["reference_cuda_eager"] = {"value": ev3, "unit": UNIT, "speedup_e2e": round(r["e2e_value"] / ev3, 1),
+                                                     "sample": f"oracle port as PyTorch CUDA eager, B={sb}, {max(1, min(G, a.eager_samples))} of {G} samples "
+                                                               f"timed ({edt3:.2f} s), scaled"}
+                except Exception as exc:
+                    entry["reference_cuda_eager"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            shipped_T3.append(entry)
+        if cpu_baseline is not None:
+            cpu_baseline["sample"] += " || shipped shape T=3: " + "; ".join(
+                f"B={e['windows_per_gpu_per_step']}: {e['e2e']['value']:.0f} windows/s e2e vs CUDA-eager "
+                f"{e.get('reference_cuda_eager', {}).get('value', float('nan')):.0f} ({e.get('reference_cuda_eager', {}).get('speedup_e2e', 'n/a')}x)"
+                for e in shipped_T3)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(a),
             "window_steps_per_sec": value * G * (N - 1),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": B * 4,
-                    "ms_per_step": e2e_s * 1e3, "api": "mcd_score_windows_host (pinned host windows in, host scores out)"},
-            "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "ingest": ingest, "kernels": kernels}
-    print(json.dumps(line), flush=True)
+                    "ms_per_step": e2e_s * 1e3,
+                    "api": "mcd_score_windows_host (pinned host windows in, host scores out)" +
+                           (" + the all-gather of scores (device) and its copy back to the host" if world > 1 else "")},
+            "gpu_launches": launches, "clocks": clocks_summary, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "shipped_T3": shipped_T3, "ingest": ingest, "kernels": kernels}
+    _emit(out_fd, line)
     if world > 1:
         dist.destroy_process_group()
 

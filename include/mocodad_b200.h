@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 3
+#define MCD_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define MCD_API __attribute__((visibility("default")))
@@ -67,6 +67,11 @@ typedef struct mcd_config {
   int32_t noise_steps;     /* noise_steps N: the loop runs i = N-1 .. 1                         */
   int32_t loss_fn;         /* mcd_loss_fn                                                       */
   int32_t device;          /* CUDA device ordinal                                               */
+  /* Latent variant (models/mocodad_latent.py, YAML keys latent_embedding_dim / hidden_sizes; selected by the presence of
+   * `diffusion_on_latent`, eval_MoCoDAD.py:24).  latent_dim == 0: diffusion on the poses (the fields below are ignored). */
+  int32_t latent_dim;      /* latent_embedding_dim (64); 0 = pose-space model                    */
+  int32_t n_hidden;        /* len(hidden_sizes), 1..8                                            */
+  int32_t hidden[8];       /* hidden_sizes ([64,128,128,64]); the last must equal latent_dim     */
 } mcd_config;
 
 typedef struct mcd_model mcd_model;
@@ -189,6 +194,26 @@ MCD_API int mcd_reverse_diffusion(const mcd_model* m, const float* d_data, int64
                           const float* d_noise, uint64_t seed, int64_t first_window,
                           float* d_losses, float* d_best, float* d_worst, float* d_x0,
                           void* d_ws, size_t ws_bytes, void* stream);
+
+/* ---- f4: the latent variant, MoCoDADlatent.forward at stage 'diffusion' (models/mocodad_latent.py:69-132) --------------
+ * (handles created with cfg.latent_dim > 0; such a handle carries the down half of the denoiser -- STSE_Unet,
+ *  models/stsae/stsae_unet.py:182-246 -- plus the MLP Denoiser, models/common/components.py:203-291, and serves only
+ *  mcd_cond_encode and the three calls below.)
+ * mcd_latent_encode: conditioning embedding (optional output d_cond_emb [B,E]) and latent code d_code [B,latent] of the
+ *   corrupt frames: STSE_Unet.forward at the constant step t = -1 (mocodad_latent.py:91-100).
+ * mcd_latent_denoise: one Denoiser.forward call (components.py:264-291) on d_x [n,latent] at step t; vector v uses
+ *   conditioning row v % cond_B.  d_eps [n,latent].  Parity tap.
+ * mcd_latent_reverse_diffusion: the whole forward: encode, then per sample x_T and noise_steps-1 denoiser calls + DDPM updates
+ *   on vectors, loss against the latent code, aggregation.
+ *     d_noise  NULL (Philox) or [G, N-1, B, latent]: slot 0 = x_T, slot k = z after the k-th call
+ *     d_losses [G,B] or NULL; d_best / d_worst [B] or NULL; d_x0 [G,B,latent] or NULL; d_code [B,latent] or NULL (output) */
+MCD_API int mcd_latent_encode(const mcd_model* m, const float* d_data, int64_t B, float* d_cond_emb, float* d_code,
+                      void* d_ws, size_t ws_bytes, void* stream);
+MCD_API int mcd_latent_denoise(const mcd_model* m, const float* d_x, int64_t n, int32_t t, const float* d_cond_emb,
+                       int64_t cond_B, float* d_eps, void* stream);
+MCD_API int mcd_latent_reverse_diffusion(const mcd_model* m, const float* d_data, int64_t B, int32_t G, const float* d_noise,
+                                 uint64_t seed, int64_t first_window, float* d_losses, float* d_best, float* d_worst,
+                                 float* d_x0, float* d_code, void* d_ws, size_t ws_bytes, void* stream);
 
 /* Same call for HOST buffers: H2D of h_data, the loop, D2H of the [B] 'best' scores, one
  * stream sync.  Allocates (and caches on the handle) its own device scratch and stream.  This is

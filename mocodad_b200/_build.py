@@ -17,7 +17,8 @@ CSRC = os.path.join(PKG, "csrc")
 LIB_PATH = os.path.join(PKG, "libmocodad_b200.so")
 STAMP = LIB_PATH + ".stamp"
 SOURCES = ("mcd_api.cu",)
-HEADERS = ("mcd_kernels.cuh", "mcd_block_tc.cuh", "mcd_edge_blocks.cuh", os.path.join(ROOT, "include", "mocodad_b200.h"))
+HEADERS = ("mcd_kernels.cuh", "mcd_block_tc.cuh", "mcd_edge_blocks.cuh", "mcd_latent.cuh",
+           os.path.join(ROOT, "include", "mocodad_b200.h"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

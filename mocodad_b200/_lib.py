@@ -23,10 +23,12 @@ class McdConfig(C.Structure):
         ("n_frames_cond", C.c_int32), ("cond_first", C.c_int32), ("embedding_dim", C.c_int32),
         ("cond_h_dim", C.c_int32), ("cond_channels", C.c_int32 * 3), ("noise_steps", C.c_int32),
         ("loss_fn", C.c_int32), ("device", C.c_int32),
+        ("latent_dim", C.c_int32), ("n_hidden", C.c_int32), ("hidden", C.c_int32 * 8),
     ]
 
 
 MCD_OK = 0
+ABI_VERSION = 4   # MCD_ABI_VERSION in include/mocodad_b200.h
 STATUS_NAMES = {0: "MCD_OK", -1: "MCD_ERR_INVALID_ARG", -2: "MCD_ERR_UNSUPPORTED",
                 -3: "MCD_ERR_NOT_FINALIZED", -4: "MCD_ERR_MISSING_TENSOR", -5: "MCD_ERR_CUDA",
                 -6: "MCD_ERR_WORKSPACE"}
@@ -66,6 +68,11 @@ SIGNATURES = {
     "mcd_reverse_diffusion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_uint64,
                                         C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_size_t, C.c_void_p]),
+    "mcd_latent_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mcd_latent_denoise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "mcd_latent_reverse_diffusion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_uint64, C.c_int64,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                               C.c_void_p]),
     "mcd_score_windows_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_int64,
                                          C.c_void_p]),
     "mcd_launch_count": (C.c_int64, [C.c_void_p]),
@@ -108,8 +115,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.mcd_abi_version() != 3:
-        raise ImportError(f"{path}: ABI version {lib.mcd_abi_version()} != 3 (stale build?)")
+    if lib.mcd_abi_version() != ABI_VERSION:
+        raise ImportError(f"{path}: ABI version {lib.mcd_abi_version()} != {ABI_VERSION} (stale build?)")
     _LIB = lib
     return lib
 

@@ -7,6 +7,7 @@
 #include "mcd_kernels.cuh"
 #include "mcd_block_tc.cuh"
 #include "mcd_edge_blocks.cuh"
+#include "mcd_latent.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -74,6 +75,8 @@ enum Slot {
   SLOT_XFORM,                           // dataset-item expansion (affine transforms of the base windows)
   SLOT_NORM,                            // window ingest: bounding-box-centre coordinates per frame row (unit: frame rows)
   SLOT_ITEMS,                           // window ingest: frame rows -> robust-scaled, transformed dataset items
+  SLOT_LATENT,                          // latent variant: the MLP denoiser + DDPM loop on latent vectors (unit: vectors)
+  SLOT_TTD,                             // latent variant: to_time_dim, the linear map onto the latent space
   SLOT_COUNT
 };
 const char* kSlotNames[SLOT_COUNT] = {
@@ -81,7 +84,8 @@ const char* kSlotNames[SLOT_COUNT] = {
     "st_gcnnsd3.1",  "st_gcnnsu4.0", "st_gcnnsu4.1", "st_gcnnsu3.0", "st_gcnnsu3.1", "down1",
     "down2",         "up3",          "up2",          "ddpm_step",    "randn",        "window_loss",
     "best_worst",    "cond.enc0",    "cond.enc1",    "cond.enc2",    "cond.enc3",    "cond.btlnk",
-    "tap_transpose", "time_embedding", "expand_transforms", "normalize_frames", "build_items"};
+    "tap_transpose", "time_embedding", "expand_transforms", "normalize_frames", "build_items",
+    "latent_diffusion", "latent.to_time_dim"};
 
 constexpr int nw_for(int T, int V0) {  // windows per CTA tile: ~408 (frame,joint) rows at the widest level
   return (408 / (T * V0)) > 0 ? 408 / (T * V0) : 1;
@@ -108,7 +112,6 @@ struct mcd_model {
   int T = 0, Tc = 0, t0_corrupt = 0, t0_cond = 0, E = 0, N = 0;
   int num_sms = 0;
   bool finalized = false;
-  bool use_tc = true;  // tensor-core channel contraction for the dense blocks (MCD_DISABLE_TC=1 turns it off)
   std::map<std::string, std::vector<float>> tensors;
   float* d_arena = nullptr;
   size_t arena_floats = 0;
@@ -117,7 +120,15 @@ struct mcd_model {
   PackedResample rs[kNumResample];
   const float* d_btl_W = nullptr;
   const float* d_btl_b = nullptr;
-  const float* d_pos = nullptr;  // [N][E]
+  const float* d_pos = nullptr;  // [N + 1][E]: pos_encoding(t) for t = 0..N-1, row N = the constant step -1 of the latent encoder
+  // latent variant (cfg.latent_dim > 0): down half of the denoiser + to_time_dim + the MLP denoiser
+  bool latent = false;
+  int n_blocks = kNumUnetBlocks, n_rs = kNumResample;  // denoiser blocks / joint resamples this handle carries (7 / 2 when latent)
+  LatentNet lat{};
+  const float* d_lat_img = nullptr;
+  const float* d_coef = nullptr;   // [N][3]
+  const float* d_ttd_W = nullptr;  // to_time_dim.weight re-indexed to planar-4 order, [K][L]
+  const float* d_ttd_b = nullptr;
   std::vector<float> beta, alpha, alpha_hat;
   // per-window workspace (floats)
   size_t ws_buf = 0, ws_d1 = 0, ws_d2 = 0, ws_x = 0, ws_emb = 0;
@@ -210,16 +221,16 @@ int block_op(int action, const mcd_model* m, int slot, const BlockWeights* w, co
   return launch_block<Cfg>(m, slot, *w, *io, s);
 }
 
-// The dense middle blocks: tensor-core contraction (mcd_block_tc.cuh) unless disabled, else the FMA-pipe kernel.
+// The dense middle blocks: 1x1 channel contraction on the tensor cores (mcd_block_tc.cuh).
 template <int T, int V, int CIN, int COUT>
 int dense_block_op(int action, const mcd_model* m, int slot, const BlockWeights* w, const BlockIO* io, cudaStream_t s) {
   using Tc = TcCfg<T, V, CIN, COUT, nw_for(T, 17)>;
   static_assert(Tc::SMEM_BYTES <= 227 * 1024, "tensor-core block kernel exceeds the 227 KB shared memory of an sm_100 CTA");
   if (action == 0) {
     CUDA_TRY(cudaFuncSetAttribute(stgcn_block_tc_kernel<Tc>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Tc::SMEM_BYTES)));
-    return block_op<T, V, CIN, COUT, true, IN_CL, OUT_CL>(0, m, slot, w, io, s);
+    return MCD_OK;
   }
-  if (!m->use_tc || w->Bop == nullptr) return block_op<T, V, CIN, COUT, true, IN_CL, OUT_CL>(1, m, slot, w, io, s);
+  if (w->Bop == nullptr) return fail(MCD_ERR_UNSUPPORTED, "block %s was not packed for the tensor-core kernel", kSlotNames[slot]);
   if (io->n <= 0) return MCD_OK;
   const int64_t ntiles = (io->n + Tc::NW - 1) / Tc::NW;
   const int grid = int(ntiles < m->num_sms ? ntiles : m->num_sms);
@@ -394,15 +405,20 @@ size_t carve_bytes(const mcd_model* m, int64_t n) {
 }
 
 // ---- the denoiser ----------------------------------------------------------------------------
+// Where the 2-channel input of the first block lives: element (w, c, t, v) = x[w*sn + c*sc + (t + t0)*17 + v]
+struct InputView { int64_t sn; int32_t sc, t0; };
+
 int unet_forward_impl(const mcd_model* m, const float* d_x, int64_t n, int t, const float* d_cond, int64_t condB,
                       int64_t w0, float* d_eps, const Workspace& ws, cudaStream_t s, const char* tap, float* tap_out,
-                      const DdpmArgs* fuse_ddpm = nullptr) {
+                      const DdpmArgs* fuse_ddpm = nullptr, const InputView* view = nullptr, const float** down_out = nullptr) {
   // fuse_ddpm: the last block applies the DDPM update and writes x_{t-1} over d_x in place (d_eps is not produced)
-  if (t < 0 || t >= m->N) return fail(MCD_ERR_INVALID_ARG, "step t=%d outside [0,%d)", t, m->N);
+  // down_out:  run the down half only (STSE_Unet._downscale, stsae_unet.py:182-219) and return its output buffer
+  if (t < -1 || t >= m->N || (t == -1 && !m->latent)) return fail(MCD_ERR_INVALID_ARG, "step t=%d outside [0,%d)", t, m->N);
+  if (m->latent && down_out == nullptr) return fail(MCD_ERR_UNSUPPORTED, "a latent-variant handle carries only the down half of the denoiser");
   const int T = m->T;
   BlockIO io{};
   io.n = n;
-  io.pos = m->d_pos + size_t(t) * m->E;
+  io.pos = m->d_pos + size_t(t < 0 ? m->N : t) * m->E;
   io.cond = d_cond;
   io.condB = condB > 0 ? condB : 1;
   io.w0 = w0;
@@ -422,7 +438,10 @@ int unet_forward_impl(const mcd_model* m, const float* d_x, int64_t n, int t, co
     io.out = out;
     io.in_sn = 0; io.in_sc = 0; io.in_t0 = 0; io.xres = nullptr;
     io.emb_off = m->emb_off[idx];
-    if (idx == 0) { io.in_sn = int64_t(2) * T * 17; io.in_sc = T * 17; }
+    if (idx == 0) {
+      io.in_sn = int64_t(2) * T * 17; io.in_sc = T * 17;
+      if (view != nullptr) { io.in_sn = view->sn; io.in_sc = view->sc; io.in_t0 = view->t0; }
+    }
     if (idx == kNumUnetBlocks - 1) {
       io.xres = (tap != nullptr && strcmp(tap, kUnetBlocks[idx].name) == 0) ? nullptr : d_x;
       if (io.xres == nullptr) io.out = tap_out;  // the layer's own output, reference layout
@@ -444,17 +463,21 @@ int unet_forward_impl(const mcd_model* m, const float* d_x, int64_t n, int t, co
     return launch_resample(m, idx, in, skip, out, n, C, s);
   };
 
-  {  // Linear(SiLU(pos(t) + cond)) of all 11 blocks, all windows (stsgcn.py:112-114)
+  {  // Linear(SiLU(pos(t) + cond)) of all 11 blocks (stsgcn.py:112-114): one row per conditioning row (the G samples of a
+     // window share it), or one row per window when the conditioning batch is larger than this launch
     const EmbTable& tb = m->emb_table;
     const size_t smem = (size_t(m->E) * tb.total + tb.total + size_t(kEmbWin) * m->E) * sizeof(float);
-    const int grid = grid_for(n, kEmbWin, m->num_sms, 2);
+    const bool shared_rows = d_cond == nullptr || io.condB <= n;
+    const int64_t rows = shared_rows ? (d_cond == nullptr ? 1 : io.condB) : n;
+    const int grid = grid_for(rows, kEmbWin, m->num_sms, 2);
     {
-      LaunchScope ls(m, SLOT_EMB, n, s);
-      time_embedding_kernel<<<grid, kEmbThreads, smem, s>>>(tb, io.pos, io.cond, io.condB, io.w0, n, m->E, ws.emb);
+      LaunchScope ls(m, SLOT_EMB, rows, s);
+      time_embedding_kernel<<<grid, kEmbThreads, smem, s>>>(tb, io.pos, io.cond, io.condB, shared_rows ? 0 : io.w0, rows, m->E, ws.emb);
     }
     MCD_TRY(check_launch("time_embedding"));
     io.emb = ws.emb;
     io.emb_stride = tb.total;
+    io.emb_mod = shared_rows ? rows : 0;
   }
   // models/stsae/stsae_unet.py:182-219 (_downscale), :365-403 (_upscale)
   MCD_TRY(block(0, d_x, ws.bufA));
@@ -466,6 +489,7 @@ int unet_forward_impl(const mcd_model* m, const float* d_x, int64_t n, int t, co
   MCD_TRY(resample(1, ws.d2, nullptr, ws.bufA, 64));
   MCD_TRY(block(5, ws.bufA, ws.bufB));
   MCD_TRY(block(6, ws.bufB, ws.bufA));
+  if (down_out != nullptr) { *down_out = ws.bufA; return MCD_OK; }
   MCD_TRY(resample(2, ws.bufA, ws.d2, ws.bufB, 64));
   MCD_TRY(block(7, ws.bufB, ws.bufA));
   MCD_TRY(block(8, ws.bufA, ws.bufB));
@@ -547,6 +571,21 @@ int launch_best(const mcd_model* m, const float* losses, float* best, float* wor
     best_worst_kernel<<<grid_for(B, kThreads, 1 << 20, 1), kThreads, 0, s>>>(losses, best, worst, B, G);
   }
   return check_launch("best_worst");
+}
+
+// ---- latent variant --------------------------------------------------------------------------
+size_t latent_smem_bytes(const LatentNet& net) {
+  return sizeof(float) * (size_t((net.total + 3) & ~3) + 2 * size_t(kLatVec) * net.maxw + size_t(kLatVec) * net.L + size_t(kLatVec) * net.E);
+}
+
+int launch_latent(const mcd_model* m, const LatentArgs& a, cudaStream_t s) {
+  const int64_t ntiles = (a.nv + kLatVec - 1) / kLatVec;
+  const int grid = int(ntiles < m->num_sms ? ntiles : m->num_sms);
+  {
+    LaunchScope ls(m, SLOT_LATENT, a.nv, s);
+    latent_diffusion_kernel<<<grid, kLatThreads, latent_smem_bytes(m->lat), s>>>(m->lat, a);
+  }
+  return check_launch("latent_diffusion");
 }
 
 // ---- weight packing --------------------------------------------------------------------------
@@ -839,10 +878,22 @@ int mcd_model_create(const mcd_config* cfg, mcd_model** out) {
   if (cfg->noise_steps < 1 || cfg->noise_steps > 65535) return fail(MCD_ERR_INVALID_ARG, "noise_steps=%d", cfg->noise_steps);
   if (cfg->loss_fn < 0 || cfg->loss_fn > 2) return fail(MCD_ERR_INVALID_ARG, "loss_fn=%d", cfg->loss_fn);
   if (2 * T * 17 > 65535) return fail(MCD_ERR_UNSUPPORTED, "window too large for the Philox element counter");
+  if (cfg->latent_dim != 0) {  // models/mocodad_latent.py:25-27, 49-56
+    if (cfg->latent_dim < 4 || cfg->latent_dim > kMaxE || (cfg->latent_dim & 3))
+      return fail(MCD_ERR_UNSUPPORTED, "latent_embedding_dim=%d (supported: multiples of 4 up to %d)", cfg->latent_dim, kMaxE);
+    if (cfg->n_hidden < 1 || cfg->n_hidden > kLatMaxLayers) return fail(MCD_ERR_UNSUPPORTED, "hidden_sizes of length %d (1..%d)", cfg->n_hidden, kLatMaxLayers);
+    for (int i = 0; i < cfg->n_hidden; ++i)
+      if (cfg->hidden[i] < 4 || (cfg->hidden[i] & 3) || cfg->hidden[i] > 1024)
+        return fail(MCD_ERR_UNSUPPORTED, "hidden_sizes[%d]=%d (supported: multiples of 4 up to 1024)", i, cfg->hidden[i]);
+    if (cfg->hidden[cfg->n_hidden - 1] != cfg->latent_dim)
+      return fail(MCD_ERR_INVALID_ARG, "hidden_sizes[-1]=%d must equal latent_embedding_dim=%d (the denoiser predicts noise of the latent's shape)",
+                  cfg->hidden[cfg->n_hidden - 1], cfg->latent_dim);
+    if (cfg->n_frames_cond == 0) return fail(MCD_ERR_UNSUPPORTED, "the latent variant requires the 'inject' conditioning strategy (mocodad_latent.py:31)");
+  }
   mcd_model* m = new mcd_model();
   m->cfg = *cfg;
-  const char* no_tc = getenv("MCD_DISABLE_TC");
-  m->use_tc = !(no_tc != nullptr && no_tc[0] == '1');
+  m->latent = cfg->latent_dim != 0;
+  if (m->latent) { m->n_blocks = 7; m->n_rs = 2; }
   m->T = T;
   m->Tc = cfg->n_frames_cond;
   m->t0_cond = cfg->cond_first ? 0 : T;
@@ -858,7 +909,7 @@ int mcd_model_create(const mcd_config* cfg, mcd_model** out) {
   m->ws_d2 = size_t(64) * T * 12;
   m->ws_x = size_t(2) * T * 17;
   m->ws_emb = 0;
-  for (int i = 0; i < kNumUnetBlocks; ++i) m->ws_emb += kUnetBlocks[i].cout;
+  for (int i = 0; i < m->n_blocks; ++i) m->ws_emb += kUnetBlocks[i].cout;
   *out = m;
   return MCD_OK;
 }
@@ -877,13 +928,13 @@ int mcd_model_finalize(mcd_model* m) {
   std::string missing;
   BlockOffsets uo[kNumUnetBlocks], eo[kNumEncBlocks];
   bool ok = true;
-  for (int i = 0; i < kNumUnetBlocks; ++i) {
+  for (int i = 0; i < m->n_blocks; ++i) {
     const BlockShape& b = kUnetBlocks[i];
     ok = pack_block(m, &ar, std::string("model.") + b.name + ".", b.cin, b.cout, m->T, kPyramid[b.level], true, m->E, &m->unet[i],
                     &uo[i], &missing) && ok;
   }
   size_t rsW[kNumResample] = {}, rsb[kNumResample] = {};
-  for (int i = 0; i < kNumResample; ++i) {
+  for (int i = 0; i < m->n_rs; ++i) {
     const int vin = kPyramid[kResample[i].lin], vout = kPyramid[kResample[i].lout];
     const std::string p = std::string("model.") + kResample[i].name + ".block.";
     auto* W = find(m, p + "0.weight", size_t(vout) * vin, &missing);
@@ -925,9 +976,70 @@ int mcd_model_finalize(mcd_model* m) {
       ok = false;
     }
   }
+  // latent variant: to_time_dim (stsae_unet.py:62-64, 241-244) + the MLP denoiser (components.py:231-245), BatchNorm1d folded
+  size_t ttdW = 0, ttdb = 0, lat_img = 0, coef_off = 0;
+  if (m->latent) {
+    const int C = kUnetBlocks[6].cout, P = m->T * kPyramid[2], K = C * P, L = m->cfg.latent_dim;
+    auto* W = find(m, "model.to_time_dim.weight", size_t(L) * K, &missing);
+    auto* b = find(m, "model.to_time_dim.bias", L, &missing);
+    if (W && b) {  // torch.flatten(fd1, 1) is [C,T,V] row-major; the block output is planar-4 [C/4][P][4]
+      ttdW = ar.alloc(size_t(K) * L);
+      ttdb = ar.alloc(L);
+      for (int c = 0; c < C; ++c)
+        for (int p = 0; p < P; ++p)
+          for (int l = 0; l < L; ++l) ar.h[ttdW + ((size_t(c / 4) * P + p) * 4 + c % 4) * L + l] = (*W)[size_t(l) * K + size_t(c) * P + p];
+      for (int l = 0; l < L; ++l) ar.h[ttdb + l] = (*b)[l];
+    } else {
+      ok = false;
+    }
+    LatentNet& net = m->lat;
+    net = LatentNet{};
+    net.n_layers = m->cfg.n_hidden; net.L = L; net.E = m->E; net.maxw = L;
+    int in = L, total = 0;
+    for (int i = 0; i < net.n_layers; ++i) {
+      const int out = m->cfg.hidden[i];
+      net.in[i] = in; net.out[i] = out; net.relu[i] = i + 1 < net.n_layers;
+      net.w_off[i] = total; total += in * out;
+      net.b_off[i] = total; total += out;
+      net.wc_off[i] = total; total += m->E * out;
+      net.bc_off[i] = total; total += out;
+      if (out > net.maxw) net.maxw = out;
+      if (i + 1 < net.n_layers) in = out;  // components.py:245: the input width advances only past non-final layers
+    }
+    net.total = total;
+    lat_img = ar.alloc(total);
+    for (int i = 0; i < net.n_layers && ok; ++i) {
+      char p[96];
+      const bool last = i + 1 == net.n_layers;
+      snprintf(p, sizeof(p), last ? "denoiser.net.%d." : "denoiser.net.%d.0.", i);
+      const int fin = net.in[i], fout = net.out[i];
+      auto* Wl = find(m, std::string(p) + "weight", size_t(fout) * fin, &missing);
+      auto* bl = find(m, std::string(p) + "bias", fout, &missing);
+      std::vector<double> sc(fout, 1.0), sh(fout, 0.0);
+      bool bn_ok = true;
+      if (!last) {
+        snprintf(p, sizeof(p), "denoiser.net.%d.1.", i);
+        bn_ok = bn_fold(m, p, fout, &sc, &sh, &missing);   // BatchNorm1d, eval mode, eps = 1e-5
+      }
+      snprintf(p, sizeof(p), "denoiser.cond_layers.%d.", i);
+      auto* Wc = find(m, std::string(p) + "weight", size_t(fout) * m->E, &missing);
+      auto* bc = find(m, std::string(p) + "bias", fout, &missing);
+      if (!Wl || !bl || !Wc || !bc || !bn_ok) { ok = false; break; }
+      float* img = &ar.h[lat_img];
+      for (int k = 0; k < fin; ++k)
+        for (int o = 0; o < fout; ++o) img[net.w_off[i] + k * fout + o] = float(double((*Wl)[size_t(o) * fin + k]) * sc[o]);
+      for (int o = 0; o < fout; ++o) img[net.b_off[i] + o] = float(double((*bl)[o]) * sc[o] + sh[o]);
+      for (int e = 0; e < m->E; ++e)
+        for (int o = 0; o < fout; ++o) img[net.wc_off[i] + e * fout + o] = (*Wc)[size_t(o) * m->E + e];
+      for (int o = 0; o < fout; ++o) img[net.bc_off[i] + o] = (*bc)[o];
+    }
+    coef_off = ar.alloc(size_t(m->N) * 3);
+    for (int t = 1; t < m->N; ++t) mcd_ddpm_coefficients(m->N, t, &ar.h[coef_off + 3 * t], &ar.h[coef_off + 3 * t + 1], &ar.h[coef_off + 3 * t + 2]);
+  }
   if (!ok) return fail(MCD_ERR_MISSING_TENSOR, "state_dict entry missing or mis-sized: %s", missing.c_str());
-  const size_t pos_off = ar.alloc(size_t(m->N) * m->E);
+  const size_t pos_off = ar.alloc(size_t(m->N + 1) * m->E);
   for (int t = 0; t < m->N; ++t) mcd_pos_encoding(t, m->E, &ar.h[pos_off + size_t(t) * m->E]);
+  mcd_pos_encoding(-1, m->E, &ar.h[pos_off + size_t(m->N) * m->E]);   // mocodad_latent.py:96: constant step of the latent encoder
 
   CUDA_TRY(cudaSetDevice(m->cfg.device));
   int sms = 0;
@@ -937,11 +1049,11 @@ int mcd_model_finalize(mcd_model* m) {
   CUDA_TRY(cudaMalloc(&m->d_arena, ar.h.size() * sizeof(float)));
   m->arena_floats = ar.h.size();
   CUDA_TRY(cudaMemcpy(m->d_arena, ar.h.data(), ar.h.size() * sizeof(float), cudaMemcpyHostToDevice));
-  for (int i = 0; i < kNumUnetBlocks; ++i) bind_block(&m->unet[i], uo[i], m->d_arena);
+  for (int i = 0; i < m->n_blocks; ++i) bind_block(&m->unet[i], uo[i], m->d_arena);
   {
     EmbTable& tb = m->emb_table;
     tb.nblocks = 0; tb.total = 0;
-    for (int i = 0; i < kNumUnetBlocks; ++i) {
+    for (int i = 0; i < m->n_blocks; ++i) {
       const int k = tb.nblocks++;
       tb.WEt[k] = m->unet[i].w.WEt; tb.bE[k] = m->unet[i].w.bE;
       tb.cout[k] = kUnetBlocks[i].cout; tb.off[k] = tb.total;
@@ -952,15 +1064,24 @@ int mcd_model_finalize(mcd_model* m) {
     if (smem > 200 * 1024) return fail(MCD_ERR_UNSUPPORTED, "embedding_dim %d too large for the time-embedding kernel", m->E);
     CUDA_TRY(cudaFuncSetAttribute(time_embedding_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   }
-  for (int i = 0; i < kNumResample; ++i) { m->rs[i].W = m->d_arena + rsW[i]; m->rs[i].b = m->d_arena + rsb[i]; }
+  for (int i = 0; i < m->n_rs; ++i) { m->rs[i].W = m->d_arena + rsW[i]; m->rs[i].b = m->d_arena + rsb[i]; }
+  if (m->latent) {
+    m->d_ttd_W = m->d_arena + ttdW; m->d_ttd_b = m->d_arena + ttdb;
+    m->d_lat_img = m->d_arena + lat_img; m->d_coef = m->d_arena + coef_off;
+    const size_t smem = latent_smem_bytes(m->lat);
+    if (smem > 227 * 1024)
+      return fail(MCD_ERR_UNSUPPORTED, "the MLP denoiser (%d weights) does not fit the %d KB of shared memory the latent kernel keeps it in",
+                  m->lat.total, 227);
+    CUDA_TRY(cudaFuncSetAttribute(latent_diffusion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  }
   if (m->Tc > 0) {
     for (int i = 0; i < kNumEncBlocks; ++i) bind_block(&m->enc[i], eo[i], m->d_arena);
     m->d_btl_W = m->d_arena + btlW;
     m->d_btl_b = m->d_arena + btlb;
   }
   m->d_pos = m->d_arena + pos_off;
-  for (int i = 0; i < kNumUnetBlocks; ++i) MCD_TRY(unet_block_dispatch(0, m->T, i, m, nullptr, nullptr, nullptr));
-  for (int i = 0; i < kNumResample; ++i) MCD_TRY(resample_dispatch(0, m, i, nullptr, nullptr, nullptr, 0, 0, nullptr));
+  for (int i = 0; i < m->n_blocks; ++i) MCD_TRY(unet_block_dispatch(0, m->T, i, m, nullptr, nullptr, nullptr));
+  for (int i = 0; i < m->n_rs; ++i) MCD_TRY(resample_dispatch(0, m, i, nullptr, nullptr, nullptr, 0, 0, nullptr));
   if (m->Tc > 0)
     for (int i = 0; i < kNumEncBlocks; ++i) MCD_TRY(enc_block_dispatch(0, m->Tc, i, m, nullptr, nullptr, nullptr));
   m->finalized = true;
@@ -997,6 +1118,7 @@ int mcd_cond_encode(const mcd_model* m, const float* d_data, int64_t B, float* d
 int mcd_unet_forward(const mcd_model* m, const float* d_x, int64_t n, int32_t t, const float* d_cond_emb, int64_t cond_B,
                      float* d_eps, void* d_ws, size_t ws_bytes, void* stream) {
   MCD_TRY(check_ready(m));
+  if (m->latent) return fail(MCD_ERR_UNSUPPORTED, "mcd_unet_forward: a latent-variant handle carries only the down half of the denoiser (use mcd_latent_*)");
   if (d_x == nullptr || d_eps == nullptr || d_ws == nullptr || n < 0) return fail(MCD_ERR_INVALID_ARG, "mcd_unet_forward: bad argument");
   if (n == 0) return MCD_OK;
   if (ws_bytes < carve_bytes(m, n)) return fail(MCD_ERR_WORKSPACE, "workspace %zu B < %zu B needed for %lld windows", ws_bytes, carve_bytes(m, n), (long long)n);
@@ -1010,13 +1132,15 @@ int mcd_unet_tap(const mcd_model* m, const float* d_x, int64_t n, int32_t t, con
   if (d_x == nullptr || d_out == nullptr || d_ws == nullptr || layer_name == nullptr || n < 0)
     return fail(MCD_ERR_INVALID_ARG, "mcd_unet_tap: bad argument");
   bool known = false;
-  for (auto& b : kUnetBlocks) known = known || strcmp(b.name, layer_name) == 0;
-  for (auto& r : kResample) known = known || strcmp(r.name, layer_name) == 0;
+  for (int i = 0; i < m->n_blocks; ++i) known = known || strcmp(kUnetBlocks[i].name, layer_name) == 0;
+  for (int i = 0; i < m->n_rs; ++i) known = known || strcmp(kResample[i].name, layer_name) == 0;
   if (!known) return fail(MCD_ERR_INVALID_ARG, "unknown denoiser layer '%s'", layer_name);
   if (n == 0) return MCD_OK;
   if (ws_bytes < carve_bytes(m, n)) return fail(MCD_ERR_WORKSPACE, "workspace %zu B < %zu B needed", ws_bytes, carve_bytes(m, n));
   Workspace ws = carve(m, static_cast<float*>(d_ws), n);
-  return unet_forward_impl(m, d_x, n, t, d_cond_emb, cond_B, 0, ws.eps, ws, static_cast<cudaStream_t>(stream), layer_name, d_out);
+  const float* down = nullptr;   // latent handles: the down half only (taps of its layers; t = -1 is the encoder's constant step)
+  return unet_forward_impl(m, d_x, n, t, d_cond_emb, cond_B, 0, ws.eps, ws, static_cast<cudaStream_t>(stream), layer_name, d_out, nullptr,
+                           nullptr, m->latent ? &down : nullptr);
 }
 
 int mcd_ddpm_step(const mcd_model* m, float* d_x, const float* d_eps, const float* d_noise, int64_t n, int32_t t,
@@ -1185,6 +1309,7 @@ int mcd_reverse_diffusion(const mcd_model* m, const float* d_data, int64_t B, in
                           int64_t first_window, float* d_losses, float* d_best, float* d_worst, float* d_x0, void* d_ws,
                           size_t ws_bytes, void* stream) {
   MCD_TRY(check_ready(m));
+  if (m->latent) return fail(MCD_ERR_UNSUPPORTED, "mcd_reverse_diffusion: latent-variant handle (use mcd_latent_reverse_diffusion)");
   if (d_data == nullptr || d_ws == nullptr || B < 0 || G < 1) return fail(MCD_ERR_INVALID_ARG, "mcd_reverse_diffusion: bad argument");
   if (B == 0) return MCD_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1242,9 +1367,105 @@ int mcd_reverse_diffusion(const mcd_model* m, const float* d_data, int64_t B, in
   return MCD_OK;
 }
 
+namespace {
+// latent code of the corrupt frames: STSE_Unet.forward at the constant step t = -1 (mocodad_latent.py:91-100; stsae_unet.py:222-246)
+int latent_encode_impl(const mcd_model* m, const float* d_data, int64_t B, const float* cond_emb, float* d_code, const Workspace& ws,
+                       cudaStream_t s) {
+  const InputView view{int64_t(2) * m->cfg.n_frames * 17, m->cfg.n_frames * 17, m->t0_corrupt};
+  const float* down = nullptr;
+  MCD_TRY(unet_forward_impl(m, d_data, B, -1, cond_emb, B, 0, nullptr, ws, s, nullptr, nullptr, nullptr, &view, &down));
+  const int K = kUnetBlocks[6].cout * m->T * kPyramid[2];
+  {
+    LaunchScope ls(m, SLOT_TTD, B, s);
+    bottleneck_kernel<<<grid_for(B * 32, kThreads, 1 << 20, 1), kThreads, 0, s>>>(down, m->d_ttd_W, m->d_ttd_b, d_code, B, K, m->cfg.latent_dim);
+  }
+  return check_launch("to_time_dim");
+}
+
+LatentArgs make_latent_args(const mcd_model* m) {
+  LatentArgs a{};
+  a.img = m->d_lat_img; a.pos = m->d_pos; a.coef = m->d_coef;
+  a.N = m->N; a.single_t = -1; a.loss_fn = m->cfg.loss_fn;
+  return a;
+}
+}  // namespace
+
+int mcd_latent_encode(const mcd_model* m, const float* d_data, int64_t B, float* d_cond_emb, float* d_code, void* d_ws, size_t ws_bytes,
+                      void* stream) {
+  MCD_TRY(check_ready(m));
+  if (!m->latent) return fail(MCD_ERR_UNSUPPORTED, "mcd_latent_encode: the handle was not created with latent_dim > 0");
+  if (d_data == nullptr || d_code == nullptr || d_ws == nullptr || B < 0) return fail(MCD_ERR_INVALID_ARG, "mcd_latent_encode: bad argument");
+  if (B == 0) return MCD_OK;
+  const size_t fixed = d_cond_emb ? 0 : align_floats(size_t(B) * m->E);
+  if (ws_bytes < fixed * sizeof(float) + carve_bytes(m, B))
+    return fail(MCD_ERR_WORKSPACE, "workspace %zu B < %zu B needed for %lld windows", ws_bytes, fixed * sizeof(float) + carve_bytes(m, B), (long long)B);
+  float* base = static_cast<float*>(d_ws);
+  float* emb = d_cond_emb ? d_cond_emb : base;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const Workspace ws = carve(m, base + fixed, B);
+  MCD_TRY(cond_encode_impl(m, d_data, B, emb, ws, s));
+  return latent_encode_impl(m, d_data, B, emb, d_code, ws, s);
+}
+
+int mcd_latent_denoise(const mcd_model* m, const float* d_x, int64_t n, int32_t t, const float* d_cond_emb, int64_t cond_B, float* d_eps,
+                       void* stream) {
+  MCD_TRY(check_ready(m));
+  if (!m->latent) return fail(MCD_ERR_UNSUPPORTED, "mcd_latent_denoise: the handle was not created with latent_dim > 0");
+  if (d_x == nullptr || d_eps == nullptr || n < 0) return fail(MCD_ERR_INVALID_ARG, "mcd_latent_denoise: bad argument");
+  if (t < 0 || t >= m->N) return fail(MCD_ERR_INVALID_ARG, "step t=%d outside [0,%d)", t, m->N);
+  if (n == 0) return MCD_OK;
+  LatentArgs a = make_latent_args(m);
+  a.cond = d_cond_emb; a.x_in = d_x; a.x_out = d_eps; a.nv = n; a.B = (d_cond_emb && cond_B > 0) ? cond_B : n; a.single_t = t;
+  return launch_latent(m, a, static_cast<cudaStream_t>(stream));
+}
+
+int mcd_latent_reverse_diffusion(const mcd_model* m, const float* d_data, int64_t B, int32_t G, const float* d_noise, uint64_t seed,
+                                 int64_t first_window, float* d_losses, float* d_best, float* d_worst, float* d_x0, float* d_code,
+                                 void* d_ws, size_t ws_bytes, void* stream) {
+  MCD_TRY(check_ready(m));
+  if (!m->latent) return fail(MCD_ERR_UNSUPPORTED, "mcd_latent_reverse_diffusion: the handle was not created with latent_dim > 0");
+  if (d_data == nullptr || d_ws == nullptr || B < 0 || G < 1) return fail(MCD_ERR_INVALID_ARG, "mcd_latent_reverse_diffusion: bad argument");
+  if (B == 0) return MCD_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t nv = int64_t(G) * B;
+  const int L = m->cfg.latent_dim;
+  float* base = static_cast<float*>(d_ws);
+  size_t fixed = 0;
+  float* cond_emb = base + fixed; fixed += align_floats(size_t(B) * m->E);
+  float* code = d_code;
+  if (code == nullptr) { code = base + fixed; fixed += align_floats(size_t(B) * L); }
+  float* losses = d_losses;
+  if (losses == nullptr) { losses = base + fixed; fixed += align_floats(size_t(nv)); }
+  if (ws_bytes < fixed * sizeof(float) + carve_bytes(m, 1))
+    return fail(MCD_ERR_WORKSPACE, "workspace %zu B cannot hold one window tile (%zu B fixed + %zu B per window)", ws_bytes,
+                fixed * sizeof(float), carve_bytes(m, 1));
+  float* tile_base = base + fixed;
+  const size_t tile_bytes = ws_bytes - fixed * sizeof(float);
+  int64_t n_tile = int64_t((tile_bytes - 7 * 256) / (per_window_floats(m) * sizeof(float)));
+  while (n_tile > 1 && carve_bytes(m, n_tile) > tile_bytes) --n_tile;
+  if (n_tile < 1) n_tile = 1;
+  if (n_tile > B) n_tile = B;
+  // condition embedding and latent code, once per batch (mocodad_latent.py:91-100)
+  for (int64_t b0 = 0; b0 < B; b0 += n_tile) {
+    const int64_t nb = (B - b0) < n_tile ? (B - b0) : n_tile;
+    const Workspace ws = carve(m, tile_base, nb);
+    const float* dp = d_data + b0 * 2 * m->cfg.n_frames * 17;
+    MCD_TRY(cond_encode_impl(m, dp, nb, cond_emb + b0 * m->E, ws, s));
+    MCD_TRY(latent_encode_impl(m, dp, nb, cond_emb + b0 * m->E, code + b0 * L, ws, s));
+  }
+  // the generated samples: every vector stays on its SM from x_T to the loss (mocodad_latent.py:102-127)
+  LatentArgs a = make_latent_args(m);
+  a.cond = cond_emb; a.code = code; a.noise = d_noise; a.x_out = d_x0; a.losses = losses;
+  a.nv = nv; a.B = B; a.first_window = first_window; a.seed = seed;
+  MCD_TRY(launch_latent(m, a, s));
+  if (d_best || d_worst) MCD_TRY(launch_best(m, losses, d_best, d_worst, B, G, s));  // mocodad.py:504-512
+  return MCD_OK;
+}
+
 int mcd_score_windows_host(mcd_model* m, const float* h_data, int64_t B, int32_t G, uint64_t seed, int64_t first_window,
                            float* h_best) {
   MCD_TRY(check_ready(m));
+  if (m->latent) return fail(MCD_ERR_UNSUPPORTED, "mcd_score_windows_host: latent-variant handle (use mcd_latent_reverse_diffusion)");
   if (h_data == nullptr || h_best == nullptr || B < 0 || G < 1) return fail(MCD_ERR_INVALID_ARG, "mcd_score_windows_host: bad argument");
   if (B == 0) return MCD_OK;
   CUDA_TRY(cudaSetDevice(m->cfg.device));
@@ -1379,6 +1600,15 @@ int mcd_profile_slot_cost(const mcd_model* m, int slot, double* bytes_per_window
   } else if (slot == SLOT_EMB) {
     bytes = 4.0 * (m->E + m->ws_emb);
     flops = 2.0 * m->E * m->ws_emb;
+  } else if (slot == SLOT_LATENT && m->latent) {  // per latent vector: conditioning row + latent code in, loss out; N-1 MLP calls
+    double macs = 0;
+    for (int i = 0; i < m->lat.n_layers; ++i) macs += double(m->lat.in[i] + m->E) * m->lat.out[i];
+    bytes = 4.0 * (m->E + m->lat.L + 1);
+    flops = 2.0 * macs * (m->N - 1);
+  } else if (slot == SLOT_TTD && m->latent) {
+    const double K = double(kUnetBlocks[6].cout) * m->T * kPyramid[2];
+    bytes = 4.0 * (K + m->lat.L);
+    flops = 2.0 * K * m->lat.L;
   }
   if (bytes_per_window) *bytes_per_window = bytes;
   if (flops_per_window) *flops_per_window = flops;

@@ -37,19 +37,6 @@
 #ifndef MCD_TC_TRACE
 #define MCD_TC_TRACE 0
 #endif
-#ifndef MCD_EXP_SKIP_A
-#define MCD_EXP_SKIP_A 0  // experiment only (wrong results): the A-mix warps skip their arithmetic
-#endif
-#ifndef MCD_EXP_SKIP_EPI
-#define MCD_EXP_SKIP_EPI 0  // experiment only: the epilogue warps skip TMEM loads, arithmetic and stores
-#endif
-#ifndef MCD_EXP_EPI_NOMEM
-#define MCD_EXP_EPI_NOMEM 0  // experiment only: the epilogue does its arithmetic but no global loads / stores
-#endif
-#ifndef MCD_EXP_SKIP_MMA
-#define MCD_EXP_SKIP_MMA 0  // experiment only: the MMA warp issues no MMAs (commits still arrive)
-#endif
-
 namespace mcd {
 
 constexpr int kTcMix = 128;        // threads per mix group (T-warps 0-3, A-warps 4-7)
@@ -539,7 +526,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       constexpr int NY2 = Cfg::NY2;  // Y2 / Y2lo buffer it % NY2 was last read by the MMAs of iteration it - NY2
       if (it >= NY2) WAIT(1, BAR(BAR_MMA_DONE + ((it - NY2) & 1)), uint32_t(((it - NY2) / 2) & 1));
       if (warp == 4) TRACE(1, it, 2);
-      if (active && !MCD_EXP_SKIP_A) {
+      if (active) {
         const float* sY = sY1 + s * Y1ARR;
         float* sZ = sY2 + (it % NY2) * ARR;
         float* sZlo = sY2lo + (it % NY2) * ARR;
@@ -624,7 +611,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       const uint64_t xHi = dX_0 + uint64_t(b) * ARR16, xLo = dXlo_0 + uint64_t(j % (Cfg::NXLO > 0 ? Cfg::NXLO : 1)) * ARR16;
       if (elect_one()) {
 #pragma unroll
-        for (int m = 0; m < (MCD_EXP_SKIP_MMA ? 0 : MT); ++m) {
+        for (int m = 0; m < MT; ++m) {
           const uint32_t d = d0 + m * TCOLS;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {  // two K=8 steps per 16-channel chunk: c4 planes (2h, 2h+1)
@@ -671,7 +658,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       const uint32_t acc0 = (RESCONV || chunk > 0) ? 1u : 0u;
       if (elect_one()) {
 #pragma unroll
-        for (int m = 0; m < (MCD_EXP_SKIP_MMA ? 0 : MT); ++m) {
+        for (int m = 0; m < MT; ++m) {
           const uint32_t d = d0 + m * TCOLS;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {  // two K=8 steps per 64-byte operand row
@@ -777,7 +764,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
         const int i = etid + k * kTcEpilogue;
         const int wl = i / COUT, co = i - wl * COUT;
         const int64_t w = tl * NW + wl;
-        epre[k] = (i < NW * COUT && w < io.n) ? __ldg(io.emb + w * io.emb_stride + io.emb_off + co) : 0.f;
+        epre[k] = (i < NW * COUT && w < io.n) ? __ldg(io.emb + emb_row(io.w0, w, io.emb_mod) * io.emb_stride + io.emb_off + co) : 0.f;
       }
     };
     load_emb(blockIdx.x);
@@ -797,7 +784,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       if (warp == kTcEpiWarp0) TRACE(4, ti, 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int m = 0; m < (MCD_EXP_SKIP_EPI ? 0 : MT); ++m) {
+      for (int m = 0; m < MT; ++m) {
         const int r = m * 128 + q * 32 + lane;
         const int wl = r / P;
         const int64_t w = tile * NW + wl;
@@ -811,7 +798,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
           float* op = io.out + (ok ? act_off(w, c0 >> 2, pp, COUT, P) : 0);
           if constexpr (!RESCONV) {  // identity residual: issue the loads of this column group before touching TMEM
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) xr[j4] = MCD_EXP_EPI_NOMEM ? make_float4(0.f, 0.f, 0.f, float(j4)) : ldg_nc4(ip + j4 * P * 4);  // 4-channel planes are P elements apart
+            for (int j4 = 0; j4 < 8; ++j4) xr[j4] = ldg_nc4(ip + j4 * P * 4);  // 4-channel planes are P elements apart
           }
           uint32_t acc[32];
           const long long t_ld = MCD_CLOCK();
@@ -844,7 +831,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
               v = v > 0.f ? v : slope * v;
               o[jj] = v + f4get(ec, jj);
             }
-            stg4_pred(op + j4 * P * 4, make_float4(o[0], o[1], o[2], o[3]), ok && !(MCD_EXP_EPI_NOMEM && o[0] != 12345.f));
+            stg4_pred(op + j4 * P * 4, make_float4(o[0], o[1], o[2], o[3]), ok);
           }
           PHASE(3, t_st);
         }

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(Cfg::THREADS) edge_block_kernel(const BlockWei
     for (int i = tid; i < NW * CE; i += Cfg::THREADS) {
       const int ewl = i / CE, co = i - ewl * CE;
       const int64_t ew = tile * NW + ewl;
-      sEmb[ewl][co] = ew < io.n ? __ldg(io.emb + ew * io.emb_stride + io.emb_off + co) : 0.f;
+      sEmb[ewl][co] = ew < io.n ? __ldg(io.emb + emb_row(io.w0, ew, io.emb_mod) * io.emb_stride + io.emb_off + co) : 0.f;
     }
     __syncthreads();
 

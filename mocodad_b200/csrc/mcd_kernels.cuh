@@ -41,6 +41,9 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src
 // offset (floats) of the 4-channel group g of position p of window w in a planar-4 activation tensor with C channels
 __device__ __forceinline__ int64_t act_off(int64_t w, int g, int p, int C, int P) { return ((w * (C >> 2) + g) * int64_t(P) + p) * 4; }
 
+// row of the precomputed embedding table that window w of a launch reads (BlockIO::emb_mod)
+__device__ __forceinline__ int64_t emb_row(int64_t w0, int64_t w, int64_t emb_mod) { return emb_mod > 0 ? (w0 + w) % emb_mod : w; }
+
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
@@ -119,10 +122,12 @@ struct BlockIO {
   long long* trace;   // debug: CTA 0 records (role, pair, event, clock64) quadruples here (nullptr: off)
   int trace_cap;      // capacity in records
   int32_t E;
-  // tensor-core block kernel: time/condition embedding precomputed by time_embedding_kernel, [n][emb_stride] floats,
-  // this block's COUT values at column emb_off
+  // denoiser blocks: time/condition embedding precomputed by time_embedding_kernel, [rows][emb_stride] floats, this block's
+  // COUT values at column emb_off.  The embedding depends on the window only through its conditioning row, so the table
+  // has emb_mod rows (one per conditioning row; window w reads row (w0 + w) % emb_mod) -- or, emb_mod == 0, one row per window.
   const float* emb;
   int32_t emb_stride, emb_off;
+  int64_t emb_mod;
   // last denoiser block only: apply the DDPM update to its eps and write x_{t-1} to `out` (= the x buffer, in place: every
   // element is read and written by the same thread) instead of eps; saves the round trip of eps through HBM and a launch
   int32_t fuse_ddpm;

@@ -36,7 +36,9 @@ class ScoringEngine:
     def __init__(self, *, seg_len: int, n_frames_cond: int, cond_first: bool = True, noise_steps: int,
                  loss_fn: str = "smooth_l1", embedding_dim: int = 16, h_dim: int = 32,
                  channels: Sequence[int] = (32, 16, 32), device="cuda:0", n_joints: int = N_JOINTS,
-                 num_coords: int = N_COORDS):
+                 num_coords: int = N_COORDS, latent_embedding_dim: int = 0, hidden_sizes: Sequence[int] = ()):
+        """``latent_embedding_dim`` > 0 (with ``hidden_sizes``) builds the LATENT variant's engine (models/mocodad_latent.py:
+        down half of the denoiser + MLP denoiser); it serves ``cond_encode`` and the ``latent_*`` methods only."""
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -46,10 +48,16 @@ class ScoringEngine:
         if loss_fn not in _lib.LOSS_FN:
             raise ValueError(f"unknown loss_fn {loss_fn!r}")
         ch = list(channels) + [0, 0, 0]
+        hidden = [int(h) for h in hidden_sizes]
+        if len(hidden) > 8:
+            raise _lib.McdError(-2, f"hidden_sizes of length {len(hidden)} (at most 8)")
+        self.latent_dim = int(latent_embedding_dim)
         self.cfg = McdConfig(n_coords=num_coords, n_joints=n_joints, n_frames=seg_len, n_frames_cond=n_frames_cond,
                              cond_first=int(bool(cond_first)), embedding_dim=embedding_dim, cond_h_dim=h_dim,
                              cond_channels=(C.c_int32 * 3)(*ch[:3]), noise_steps=noise_steps,
-                             loss_fn=_lib.LOSS_FN[loss_fn], device=self.device.index)
+                             loss_fn=_lib.LOSS_FN[loss_fn], device=self.device.index,
+                             latent_dim=self.latent_dim, n_hidden=len(hidden) if self.latent_dim else 0,
+                             hidden=(C.c_int32 * 8)(*(hidden + [0] * 8)[:8]))
         if n_frames_cond > 0 and len(channels) != 3:
             raise _lib.McdError(-2, f"conditioning encoder with {len(channels)} hidden layers (kernels are built for 3)")
         handle = C.c_void_p()
@@ -225,6 +233,59 @@ class ScoringEngine:
             out = torch.empty(B, dtype=torch.float32)
         check(self.lib.mcd_score_windows_host(self._h, data.data_ptr(), B, int(n_generated_samples), int(seed),
                                               int(first_window), out.data_ptr()))
+        return out
+
+    # ------------------------------------------------------------------ f4: the latent variant (models/mocodad_latent.py)
+    def latent_encode(self, data: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(conditioning embedding [B,E], latent code [B,latent]) of whole windows [B,2,seg_len,V]: ``_encode_condition`` and
+        ``STSE_Unet.forward`` at the constant step -1 on the corrupt frames (mocodad_latent.py:91-100)."""
+        B = data.shape[0]
+        self._chk(data, (B, N_COORDS, self.seg_len, N_JOINTS), "data")
+        emb, code = self._new(B, self.E), self._new(B, self.latent_dim)
+        ws = self._workspace(self.workspace_bytes(max(B, 1)))
+        with torch.cuda.device(self.device):
+            check(self.lib.mcd_latent_encode(self._h, data.data_ptr(), B, emb.data_ptr(), code.data_ptr(), ws.data_ptr(), ws.numel(),
+                                             self._stream()))
+        return emb, code
+
+    def latent_denoise(self, x: torch.Tensor, t: int, cond_emb: Optional[torch.Tensor]) -> torch.Tensor:
+        """One ``Denoiser.forward`` call (components.py:264-291): predicted noise for latent vectors x [n,latent] at step t."""
+        n = x.shape[0]
+        self._chk(x, (n, self.latent_dim), "x")
+        cb = 0
+        if cond_emb is not None:
+            cb = cond_emb.shape[0]
+            self._chk(cond_emb, (cb, self.E), "cond_emb")
+        eps = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            check(self.lib.mcd_latent_denoise(self._h, x.data_ptr(), n, int(t), _ptr(cond_emb), cb, eps.data_ptr(), self._stream()))
+        return eps
+
+    def latent_reverse_diffusion(self, data: torch.Tensor, n_generated_samples: int, *, noise: Optional[torch.Tensor] = None,
+                                 seed: int = 0, first_window: int = 0, want_losses: bool = False, want_worst: bool = False,
+                                 want_samples: bool = False) -> Dict[str, torch.Tensor]:
+        """``MoCoDADlatent.forward`` at stage 'diffusion' (mocodad_latent.py:69-132) for a batch ``data`` [B,2,seg_len,V].
+        ``noise``: None -> Philox, or [G, max(N-1,1), B, latent] in the reference's draw order (slot 0 = x_T).
+        Returns 'best' [B], 'code' [B,latent] and, on request, 'losses' [G,B], 'worst' [B], 'x0' [G,B,latent]."""
+        B, G, L = data.shape[0], int(n_generated_samples), self.latent_dim
+        self._chk(data, (B, N_COORDS, self.seg_len, N_JOINTS), "data")
+        if noise is not None:
+            self._chk(noise, (G, max(self.N - 1, 1), B, L), "noise")
+        out = {"best": self._new(B), "code": self._new(B, L)}
+        if want_losses:
+            out["losses"] = self._new(G, B)
+        if want_worst:
+            out["worst"] = self._new(B)
+        if want_samples:
+            out["x0"] = self._new(G, B, L)
+        if B == 0:
+            return out
+        ws = self._workspace(self.workspace_bytes(B) + 4 * (B * self.E + G * B) + 1024)
+        with torch.cuda.device(self.device):
+            check(self.lib.mcd_latent_reverse_diffusion(
+                self._h, data.data_ptr(), B, G, _ptr(noise), int(seed), int(first_window), _ptr(out.get("losses")),
+                out["best"].data_ptr(), _ptr(out.get("worst")), _ptr(out.get("x0")), out["code"].data_ptr(), ws.data_ptr(),
+                ws.numel(), self._stream()))
         return out
 
     # ------------------------------------------------------------------ f1: dataset items on the device

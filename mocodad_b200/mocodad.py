@@ -485,12 +485,133 @@ def _processing_data(data):
 
 
 class MoCoDADlatent(MoCoDAD):
-    """Name kept for ``eval_MoCoDAD.py:24`` (``MoCoDADlatent(args) if hasattr(args, 'diffusion_on_latent')``).  The latent
-    variant (models/mocodad_latent.py: one STSE_Unet encoder pass per batch, then an MLP denoiser over [B, latent] vectors) has
-    no CUDA path yet; its oracle is pinned (oracle/latent_port.py, tests/golden/latent_T3.npz).
-    Constructing it fails loudly instead of scoring with the wrong model."""
+    """Drop-in for ``models.mocodad_latent.MoCoDADlatent`` at stage 'diffusion' (the shipped
+    config/UBnormal/mocodad-latent_test.yaml; ``eval_MoCoDAD.py:24`` picks it when the YAML carries ``diffusion_on_latent``):
+    the diffusion runs on a ``latent_embedding_dim`` vector -- the corrupt frames go once through the down half of the denoiser
+    (STSE_Unet at the constant step -1) and ``n_generated_samples`` x ``noise_steps - 1`` calls of an MLP denoiser follow
+    (models/mocodad_latent.py:69-132).  Same 292-entry ``state_dict`` as the reference module.  Stage 'pretrain' is training
+    only and raises."""
 
     def __init__(self, args: argparse.Namespace) -> None:
-        raise NotImplementedError("MoCoDADlatent (diffusion on the latent space) is outside the B200 scoring path so far "
-                                  "(SURVEY.md section 8 row f4); use the reference for 'diffusion_on_latent' configs")
+        # mocodad_latent.py:24-28
+        self.stage = args.stage
+        self.latent_embedding_dim = args.latent_embedding_dim
+        self.hidden_sizes = args.hidden_sizes
+        self.pretrained_model_ckpt_path = args.pretrained_model_ckpt_path
+        if self.stage not in ('diffusion', 'pretrain'):
+            raise ValueError(f'Unknown stage {self.stage}')
+        if self.stage == 'pretrain':
+            raise NotImplementedError("MoCoDADlatent stage 'pretrain' is a training stage (SURVEY.md section 8 row f4); "
+                                      "train with the reference and score with stage 'diffusion' here")
+        super().__init__(args)
+        assert self.conditioning_strategy == 'inject', \
+            'Conditioning strategy must be inject. Other strategies are not supported for the latent space'
+        # mocodad_latent.py:36-38: the frozen main net comes from the pretraining checkpoint
+        if self.pretrained_model_ckpt_path:
+            self._freeze_main_net_and_load_ckpt()
 
+    def build_model(self) -> None:
+        """mocodad_latent.py:42-66 -- parameter tree of STSE_Unet (+ to_time_dim) and the MLP Denoiser."""
+        if self.conditioning_architecture not in ('AE', 'E'):
+            raise NotImplementedError(f'Conditioning architecture {self.conditioning_architecture} not implemented.')
+        if self.cond_latent_dim != self.embedding_dim:
+            raise ValueError("latent_dim must equal embedding_dim (the condition embedding is added to the time embedding)")
+        if self.n_joints != 17:
+            raise NotImplementedError(f"{self.n_joints} joints: the joint pyramid is fixed at 17/12/10 (stsae_unet.py:11)")
+        if list(self.hidden_sizes)[-1] != self.latent_embedding_dim:
+            raise ValueError("hidden_sizes[-1] must equal latent_embedding_dim: the denoiser predicts noise of the latent's shape "
+                             "(the reference's DDPM update broadcasts otherwise, mocodad_latent.py:119)")
+        self._spec = state_dict_spec(T=self.input_n_frames, T_cond=self.n_frames_condition, num_coords=self.num_coords,
+                                     embedding_dim=self.embedding_dim, h_dim=self.cond_h_dim, latent_dim=self.cond_latent_dim,
+                                     channels=self.cond_channels, conditioning_architecture=self.conditioning_architecture,
+                                     n_joints=self.n_joints, latent_embedding_dim=self.latent_embedding_dim,
+                                     hidden_sizes=self.hidden_sizes)
+        _build_param_tree(self, self._spec)
+        self._engine = None
+        self._engine_key = None
+
+    def engine(self) -> _engine.ScoringEngine:
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("MoCoDADlatent (B200) computes only on a CUDA device: move the module with .to('cuda'); "
+                               "there is no CPU fallback")
+        key = self._weights_key()
+        if self._engine is None or self._engine.device != torch.device(dev.type, dev.index if dev.index is not None else torch.cuda.current_device()):
+            self._engine = _engine.ScoringEngine(
+                seg_len=self.n_frames, n_frames_cond=self.n_frames_condition, cond_first=self._cond_first,
+                noise_steps=self.noise_steps, loss_fn=self.loss_fn_name, embedding_dim=self.embedding_dim,
+                h_dim=self.cond_h_dim, channels=self.cond_channels, device=dev, n_joints=self.n_joints,
+                num_coords=self.num_coords, latent_embedding_dim=self.latent_embedding_dim, hidden_sizes=self.hidden_sizes)
+            self._engine_key = None
+        if key != self._engine_key:
+            self._engine.load_state_dict(self.state_dict())
+            self._engine_key = key
+        return self._engine
+
+    def forward(self, input_data: List[torch.Tensor], condition_data: torch.Tensor = None, aggr_strategy: str = 'best',
+                *, return_: str = None) -> List[torch.Tensor]:
+        """mocodad_latent.py:69-132 (stage 'diffusion'): [loss and/or selected latents] + [data, transformation_idx, metadata,
+        frames].  As upstream, ``aggr_strategy`` defaults to 'best' here (the YAML key is not consulted)."""
+        tensor_data, meta_out = self._unpack_data(input_data)
+        eng = self.engine()
+        data = tensor_data.to(torch.float32).contiguous()
+        B, G, L = data.shape[0], self.n_generated_samples, self.latent_embedding_dim
+        if return_ is None:
+            if self.model_return_value is None:
+                raise ValueError('Either return_ or self.model_return_value must be set')
+            return_ = self.model_return_value
+        need_latent = return_ in ('pose', 'all')
+        noise = None
+        if self.rng_mode == "torch":   # the reference's draw order: per sample x_T (torch.randn, :104) then z (:117)
+            slots = max(self.noise_steps - 1, 1)
+            noise = torch.empty(G, slots, B, L, device=data.device)
+            for g in range(G):
+                for k in range(self.noise_steps - 1 if self.noise_steps > 1 else 1):
+                    noise[g, k] = torch.randn(B, L, device=data.device)
+        first_window = self._window_cursor
+        self._window_cursor += B
+        aggr = aggr_strategy
+        simple = aggr in ('best', 'worst') and not need_latent
+        res = eng.latent_reverse_diffusion(data, G, noise=noise, seed=self.seed, first_window=first_window,
+                                           want_losses=not simple, want_worst=(aggr == 'worst'),
+                                           want_samples=need_latent or aggr in ('all', 'mean_pose', 'median_pose', 'random'))
+        if aggr == 'random':
+            return res["x0"][np.random.randint(G)]
+        selected, loss = self._aggregate_latent(res, aggr, need_latent)
+        return self._pack_out_data(selected, loss, [tensor_data] + meta_out, return_=return_)
+
+    def _aggregate_latent(self, res, aggr: str, need_latent: bool):
+        """mocodad.py:454-520 on latent vectors (the loss target is the latent code)."""
+        if aggr in ('best', 'worst'):
+            loss = res['best'] if aggr == 'best' else res['worst']
+            sel = None
+            if need_latent:
+                losses = res['losses']
+                idx = torch.argmin(losses, dim=0) if aggr == 'best' else torch.argmax(losses, dim=0)
+                sel = res['x0'][idx, torch.arange(losses.shape[1], device=losses.device)]
+            return sel, loss
+        losses = res['losses']
+        if aggr == 'all':
+            return res['x0'].permute(1, 0, 2), losses.permute(1, 0)
+        if aggr == 'mean':
+            return None, torch.mean(losses, dim=0)
+        if aggr == 'median':
+            return None, torch.median(losses, dim=0)[0]
+        if aggr in ('mean_pose', 'median_pose'):
+            sel = torch.mean(res['x0'], dim=0) if aggr == 'mean_pose' else torch.median(res['x0'], dim=0)[0]
+            d = sel - res['code']
+            if self.loss_fn_name == 'smooth_l1':
+                per = torch.where(d.abs() < 1.0, 0.5 * d * d, d.abs() - 0.5)
+            else:
+                per = d.abs() if self.loss_fn_name == 'l1' else d * d
+            return sel, per.mean(dim=-1)
+        if 'quantile' in aggr:
+            return None, torch.quantile(losses, float(aggr.split(':')[-1]), dim=0)
+        raise ValueError(f'Unknown aggregation strategy {aggr}')
+
+    def score_trajectories(self, *a, **k):
+        raise NotImplementedError("device ingest (score_trajectories) is wired to the pose-space model; feed MoCoDADlatent batches")
+
+    def _freeze_main_net_and_load_ckpt(self) -> None:
+        """mocodad_latent.py:222-227"""
+        self.load_state_dict(torch.load(self.pretrained_model_ckpt_path, map_location='cpu')['state_dict'], strict=False)

@@ -52,9 +52,12 @@ def _cnn_layer(spec, prefix: str, vin: int, vout: int) -> None:
 
 def state_dict_spec(T: int, T_cond: int = 3, *, num_coords: int = 2, embedding_dim: int = 16, h_dim: int = 32,
                     latent_dim: int = 16, channels: Sequence[int] = (32, 16, 32),
-                    conditioning_architecture: Optional[str] = "AE", n_joints: int = 17):
+                    conditioning_architecture: Optional[str] = "AE", n_joints: int = 17,
+                    latent_embedding_dim: int = 0, hidden_sizes: Sequence[int] = ()):
     """name -> shape of ``MoCoDAD(args).state_dict()``; ``T`` = denoised frames, ``T_cond`` = conditioning
-    frames; ``conditioning_architecture`` None for 'no_condition'."""
+    frames; ``conditioning_architecture`` None for 'no_condition'.  With ``latent_embedding_dim`` > 0 the layout of
+    ``MoCoDADlatent(args)`` at stage 'diffusion' (models/mocodad_latent.py:42-56: STSE_Unet with its out layer
+    ``to_time_dim`` instead of the full U-Net, plus the MLP ``Denoiser``, models/common/components.py:231-245)."""
     spec = OrderedDict()
     a, b, c = JOINT_PYRAMID
     E = embedding_dim
@@ -84,6 +87,27 @@ def state_dict_spec(T: int, T_cond: int = 3, *, num_coords: int = 2, embedding_d
     _st_gcnn(spec, m + "st_gcnnsd3.1.", D[5], D[6], T, c, E)
     _cnn_layer(spec, m + "down1.", a, b)
     _cnn_layer(spec, m + "down2.", b, c)
+    if latent_embedding_dim:
+        spec[m + "to_time_dim.weight"] = (latent_embedding_dim, D[6] * T * c)
+        spec[m + "to_time_dim.bias"] = (latent_embedding_dim,)
+        hidden = list(hidden_sizes)
+        width = latent_embedding_dim
+        for i, nxt in enumerate(hidden):
+            p = f"denoiser.net.{i}."
+            if i == len(hidden) - 1:
+                spec[p + "weight"] = (nxt, width)
+                spec[p + "bias"] = (nxt,)
+            else:
+                spec[p + "0.weight"] = (nxt, width)
+                spec[p + "0.bias"] = (nxt,)
+                for k in BN_FIELDS:
+                    spec[p + "1." + k] = (nxt,)
+                spec[p + "1.num_batches_tracked"] = ()
+                width = nxt
+        for i, nxt in enumerate(hidden):
+            spec[f"denoiser.cond_layers.{i}.weight"] = (nxt, E)
+            spec[f"denoiser.cond_layers.{i}.bias"] = (nxt,)
+        return spec
     _st_gcnn(spec, m + "st_gcnnsu4.0.", D[6], U[0], T, b, E)
     _st_gcnn(spec, m + "st_gcnnsu4.1.", U[0], U[1], T, b, E)
     _st_gcnn(spec, m + "st_gcnnsu3.0.", U[1], U[2], T, a, E)

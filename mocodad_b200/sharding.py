@@ -36,6 +36,10 @@ def gather_scores(local: torch.Tensor, n_total: int, group: Optional[dist.Proces
     if local.numel() != hi - lo:
         raise ValueError(f"rank {rank}: expected {hi - lo} local scores, got {local.numel()}")
     width = -(-n_total // world)  # ceil
+    if n_total % world == 0:   # equal shards (the bench's weak scaling, any dataset whose size divides): no padding, no re-assembly
+        recv = torch.empty(n_total, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(recv, local.reshape(-1).contiguous(), group=group)
+        return recv
     send = torch.zeros(width, dtype=local.dtype, device=local.device)
     send[: hi - lo] = local.reshape(-1)
     recv = torch.empty(world * width, dtype=local.dtype, device=local.device)

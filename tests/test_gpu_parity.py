@@ -375,3 +375,50 @@ def test_reverse_diffusion_other_frame_counts_vs_oracle(T):
     parts = torch.cat([eng.reverse_diffusion(batch[0][a:b].to(DEV).contiguous(), G, seed=5, first_window=a)["best"]
                        for a, b in ((0, 11), (11, 37))])
     assert torch.equal(whole, parts)
+
+
+# ---- the regime bench.py times: persistent CTAs that run MANY tiles each (ring slots it % NXB, mbarrier parity bits
+# (it / NXB) & 1, TMEM accumulator-set ping-pong, residual look-ahead), compared per window with the CPU oracle.
+# T=24: one window per CTA tile, 148 CTAs -> G*B = 1 200 windows are 8.1 tiles per CTA; T=3: 8 windows per tile ->
+# G*B = 10 000 windows are 8.4 tiles per CTA.  `tile` additionally cuts the virtual batch into >= 3 passes.
+@pytest.mark.parametrize("seg_len,B,G,N,tile", [(27, 600, 2, 3, None), (27, 600, 2, 3, 444), (6, 2000, 5, 3, None),
+                                                  (6, 2000, 5, 3, 3552), (15, 700, 2, 3, None)])
+def test_many_tiles_per_cta_vs_oracle(seg_len, B, G, N, tile):
+    T = seg_len - 3
+    eng, sd = _engine(seg_len, N)
+    batch = synth.synth_batch(B, seg_len, seed=51)
+    noise = synth.synth_noise(G, N, B, T, seed=52)
+    with torch.no_grad():
+        want, _, gen = ref_port.reverse_diffusion(sd, batch[0], noise_steps=N, n_generated_samples=G, noise=noise, return_samples=True)
+        _, corrupt = ref_port.select_frames(batch[0], (0, 1, 2))
+        want_all = torch.stack([ref_port.window_loss(x, corrupt) for x in gen])
+    res = eng.reverse_diffusion(batch[0].to(DEV), G, noise=noise.to(DEV), want_losses=True, want_samples=True, tile_windows=tile)
+    np.testing.assert_allclose(_np(res["x0"]), torch.stack(gen).numpy(), rtol=0, atol=1e-4)      # every element of every window
+    np.testing.assert_allclose(_np(res["losses"]), want_all.numpy(), rtol=0, atol=1e-4)
+    np.testing.assert_allclose(_np(res["best"]), want.numpy(), rtol=0, atol=1e-4)
+    # and bit-identical to the same windows scored in one-tile-per-CTA launches (the regime the small fixtures cover)
+    unit = 148 * max(1, 408 // (T * 17))
+    small = eng.reverse_diffusion(batch[0].to(DEV), G, noise=noise.to(DEV), want_losses=True, tile_windows=unit)
+    assert torch.equal(small["losses"], res["losses"])
+
+
+@pytest.mark.parametrize("T,n", [(24, 1200), (3, 9600)])
+def test_layer_taps_with_many_tiles_per_cta_vs_oracle(T, n):
+    """Block-level taps at that size, one of every tensor-core kernel flavour: residual convolution + N-merged MMAs (sd3.1,
+    su4.1), residual convolution with single Xlo / Y2 buffers (sd1.0 at V=17), identity residual (sd2.1), wide output (sd3.0),
+    plus the joint resamples and the first / last (edge) blocks through the final eps."""
+    seg_len, N = T + 3, 10
+    eng, sd = _engine(seg_len, N)
+    batch = synth.synth_batch(n, seg_len, seed=61)
+    x0 = synth.synth_noise(1, N, n, T, seed=62)[0, 0]
+    with torch.no_grad():
+        cond, _ = ref_port.select_frames(batch[0], (0, 1, 2))
+        emb = ref_port.cond_encode(sd, cond)
+        taps = {}
+        eps = ref_port.unet_forward(sd, x0, torch.full((n,), 6, dtype=torch.long), emb, taps=taps)
+    x, demb = x0.to(DEV).contiguous(), emb.to(DEV)
+    for k in ("st_gcnnsd1.0", "st_gcnnsd2.1", "st_gcnnsd3.0", "st_gcnnsd3.1", "st_gcnnsu4.1", "st_gcnnsu3.0", "down2", "up3"):
+        want = taps[k]
+        got = eng.unet_tap(x, 6, demb, k, want.shape[1], want.shape[3])
+        np.testing.assert_allclose(_np(got), want.numpy(), rtol=0, atol=2e-5, err_msg=f"T={T} {k}")
+    np.testing.assert_allclose(_np(eng.unet_forward(x, 6, demb)), eps.numpy(), rtol=0, atol=2e-5)

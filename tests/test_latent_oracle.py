@@ -1,7 +1,7 @@
-"""Groundwork for SURVEY.md 8 row f4 (the latent variant, models/mocodad_latent.py): the CPU restatement oracle/latent_port.py
-against the fixture the UNMODIFIED MoCoDADlatent produced (oracle/make_latent_golden.py asserted bit-equality where it was
-generated; a small fp32 tolerance here allows for another CPU / BLAS build).  No CUDA path exists for this variant yet, so
-there is no gpu test: the product package must refuse it."""
+"""SURVEY.md 8 row f4 (the latent variant, models/mocodad_latent.py): the CPU restatement oracle/latent_port.py against the
+fixture the UNMODIFIED MoCoDADlatent produced (oracle/make_latent_golden.py asserted bit-equality where it was generated; a
+small fp32 tolerance here allows for another CPU / BLAS build), and the host-side surface of the product's MoCoDADlatent
+(state_dict layout, constructor contract, no CPU fallback).  The CUDA parity tests are in tests/test_latent_gpu.py."""
 from collections import OrderedDict
 
 import numpy as np
@@ -57,8 +57,45 @@ def test_latent_reverse_diffusion_losses(golden, strategy):
         np.testing.assert_allclose(sel.numpy(), g["latent_sel"], rtol=0, atol=1e-4)
 
 
-def test_product_package_refuses_the_latent_variant():
+def _latent_args(**over):
     import argparse
+    from test_module import BASE
+    cfg = dict(BASE, diffusion_on_latent=True, stage="diffusion", latent_embedding_dim=64, hidden_sizes=[64, 128, 128, 64],
+               pretrained_model_ckpt_path="", n_generated_samples=3)
+    cfg.update(over)
+    return argparse.Namespace(**cfg)
+
+
+def test_product_module_has_the_reference_state_dict_layout(golden):
+    """MoCoDADlatent(args).state_dict() == the unmodified reference module's, name by name and shape by shape."""
     from mocodad_b200 import MoCoDADlatent
-    with pytest.raises(NotImplementedError, match="latent"):
-        MoCoDADlatent(argparse.Namespace(diffusion_on_latent=True))
+    g = golden("latent_T3")
+    m = MoCoDADlatent(_latent_args())
+    sd = m.state_dict()
+    assert list(sd.keys()) == [str(n) for n in g["spec_names"]]
+    assert [",".join(map(str, v.shape)) for v in sd.values()] == [str(x) for x in g["spec_shapes"]]
+    m.load_state_dict(synth.synth_state_dict(OrderedDict((k, tuple(v.shape)) for k, v in sd.items()), seed=0), strict=True)
+
+
+def test_product_module_contract_without_a_gpu(tmp_path):
+    from mocodad_b200 import MoCoDADlatent
+    with pytest.raises(NotImplementedError, match="pretrain"):
+        MoCoDADlatent(_latent_args(stage="pretrain"))
+    with pytest.raises(ValueError):
+        MoCoDADlatent(_latent_args(stage="nope"))
+    with pytest.raises(ValueError, match="hidden_sizes"):
+        MoCoDADlatent(_latent_args(hidden_sizes=[64, 128, 32]))
+    with pytest.raises(AttributeError):          # a missing YAML key is an AttributeError, as upstream (mocodad_latent.py:24-27)
+        ns = _latent_args()
+        del ns.hidden_sizes
+        MoCoDADlatent(ns)
+    # the pretraining checkpoint is loaded with strict=False at construction (mocodad_latent.py:222-227)
+    m0 = MoCoDADlatent(_latent_args())
+    part = {k: torch.full_like(v, 0.5) for k, v in m0.state_dict().items() if k.startswith("model.st_gcnnsd1.0.tcn.0")}
+    ck = tmp_path / "pretrain.ckpt"
+    torch.save({"state_dict": part}, ck)
+    m1 = MoCoDADlatent(_latent_args(pretrained_model_ckpt_path=str(ck)))
+    assert all(torch.equal(m1.state_dict()[k], v) for k, v in part.items())
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):   # no CPU fallback
+            m1.forward(synth.synth_batch(4, 6, seed=1))
