@@ -152,6 +152,7 @@ class MoCoDAD(_Base):
         # (the reference hands them to get_dataset_and_loader, utils/dataset.py:270-331)
         self.data_dir = getattr(args, "data_dir", None)
         self.vid_res = getattr(args, "vid_res", None)
+        self.seg_stride = int(getattr(args, "seg_stride", 1) or 1)   # train split only (utils/dataset.py:308)
         # knobs new to this implementation (optional)
         self.rng_mode = getattr(args, "b200_rng", "philox")
         if self.rng_mode not in ("philox", "torch"):
@@ -417,7 +418,16 @@ class MoCoDAD(_Base):
             raise ValueError("score_trajectories needs data_dir and vid_res = [width, height] (arguments or YAML keys)")
         ts = ingest.load_trajectories(os.path.join(data_dir, ingest.split_subfolder(split), 'trajectories'))
         starts, meta, frames = ingest.window_table(ts, self.n_frames, 1)       # no strides for the test set (dataset.py:308)
-        center, scale = ingest.load_robust_scaler(self.ckpt_dir)
+        if split == 'validation' and 'UBnormal' not in data_dir:
+            # get_robust_data.py:120-123: outside UBnormal the validation split is scaled by a scaler fitted on itself
+            # (pickled as local_robust_val.pickle), not by the training run's
+            scaler = self.engine().fit_scaler_host(ts.coords, ts.lengths, vid_res, seg_stride=1)
+            import pickle
+            with open(os.path.join(self.ckpt_dir, 'local_robust_val.pickle'), 'wb') as fh:
+                pickle.dump(scaler, fh)
+            center, scale = ingest.scaler_arrays(scaler)
+        else:
+            center, scale = ingest.load_robust_scaler(self.ckpt_dir)
         if int(self.num_transforms) < 1:
             raise NotImplementedError("num_transform < 1: the reference's untransformed dataset path applies a random temporal crop "
                                       "per item (utils/dataset.py:77-83, 127-130), which has no device counterpart")
@@ -440,7 +450,10 @@ class MoCoDAD(_Base):
         if data_dir is None or vid_res is None or len(vid_res) != 2:
             raise ValueError("fit_trajectory_scaler needs data_dir and vid_res = [width, height] (arguments or YAML keys)")
         ts = ingest.load_trajectories(os.path.join(data_dir, ingest.split_subfolder(split), 'trajectories'))
-        return self.engine().fit_scaler_host(ts.coords, ts.lengths, vid_res, exp_dir=self.ckpt_dir)
+        # the train split drops trajectories too short for one STRIDED window before the fit (get_robust_data.py:44,58:
+        # input_gap = seg_stride - 1; utils/dataset.py:308 hands seg_stride to the train split only)
+        stride = self.seg_stride if 'train' in split else 1
+        return self.engine().fit_scaler_host(ts.coords, ts.lengths, vid_res, seg_stride=stride, exp_dir=self.ckpt_dir)
 
     def test_on_trajectories(self, data_dir: str = None, vid_res=None, split: str = None, batch: int = 1024) -> float:
         """``score_trajectories`` -> ``post_processing`` -> AUC: the device-ingest twin of eval_MoCoDAD.py:30-38."""

@@ -104,6 +104,19 @@ def main():
         assert fitted.scale_.dtype == sk.scale_.dtype and fitted.scale_.tobytes() == sk.scale_.tobytes(), "scale_ differs"
         print("RobustScaler fit on", len(tr), "training trajectories: bit-identical to the reference's pickle")
         out.update(train_coords=tr.coords, train_lengths=tr.lengths)
+        # a STRIDED train split (config/STC/mocodad_train.yaml: seg_stride 6): remove_short_trajectories runs with
+        # input_gap = seg_stride - 1 before the fit (get_robust_data.py:44,58), so fewer trajectories reach the scaler
+        exp_s = os.path.join(root, "exp_s3")
+        os.makedirs(exp_s)
+        run_reference(root, exp_s, "train", 6, 3)
+        with open(os.path.join(exp_s, "local_robust.pickle"), "rb") as fh:
+            sk3 = pickle.load(fh)
+        fitted3 = ingest.fit_robust_scaler(otr.bbox_centre_normalize(tr.coords, VID_RES), tr.lengths, 6, 3)
+        assert fitted3.center_.tobytes() == sk3.center_.tobytes() and fitted3.scale_.tobytes() == sk3.scale_.tobytes(), "stride-3 fit differs"
+        assert sk3.center_.tobytes() != sk.center_.tobytes(), "the strided split must drop at least one trajectory for this case to bite"
+        kept = int((tr.lengths >= 6 + 2 * 5).sum())
+        print(f"RobustScaler fit at seg_stride 3 ({kept} of {len(tr)} trajectories long enough): bit-identical to the reference's pickle")
+        out.update(center_s3=np.asarray(sk3.center_, dtype=np.float64), scale_s3=np.asarray(sk3.scale_, dtype=np.float64))
         ts = ingest.load_trajectories(os.path.join(root, "testing", "trajectories"))
         out.update(coords=ts.coords, frames=ts.frames, lengths=ts.lengths, ids=ts.ids, center=center, scale=scale,
                    vid_res=np.asarray(VID_RES, dtype=np.float32))

@@ -66,7 +66,8 @@ def test_latent_reverse_diffusion_vs_reference(golden):
     np.testing.assert_allclose(_np(res["losses"].median(0)[0]), g["loss_median"], rtol=0, atol=1e-4)
     assert torch.equal(res["best"], res["losses"].min(0)[0]) and torch.equal(res["worst"], res["losses"].max(0)[0])
     idx = res["losses"].argmin(0)
-    np.testing.assert_allclose(_np(res["x0"][idx, torch.arange(B, device=DEV)]), g["latent_sel"], rtol=0, atol=1e-4)
+    # the latent vectors themselves are O(100): 1e-4 absolute on the loss, the same relative accuracy on the vectors
+    np.testing.assert_allclose(_np(res["x0"][idx, torch.arange(B, device=DEV)]), g["latent_sel"], rtol=2e-6, atol=1e-4)
     np.testing.assert_allclose(_np(res["code"]), g["latent_code"], rtol=0, atol=2e-5)
 
 
@@ -90,7 +91,7 @@ def test_module_surface_vs_reference(golden, strategy):
         torch.randn = real
     np.testing.assert_allclose(_np(out[0]), g["loss_" + strategy], rtol=0, atol=1e-4)
     if strategy == "best":
-        np.testing.assert_allclose(_np(out[1]), g["latent_sel"], rtol=0, atol=1e-4)
+        np.testing.assert_allclose(_np(out[1]), g["latent_sel"], rtol=2e-6, atol=1e-4)
         assert len(out) == 6
     assert out[-4].shape == (B, 2, seg_len, 17)
 

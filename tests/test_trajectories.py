@@ -231,6 +231,38 @@ def test_scaler_fit_on_device_normalised_rows_matches_the_reference_pickle():
     assert np.array_equal(sk.center_.astype(np.float64), g["center"]) and np.array_equal(np.asarray(sk.scale_, np.float64), g["scale"])
 
 
+@pytest.mark.gpu
+def test_scaler_fit_of_a_strided_train_split_matches_the_reference_pickle(tmp_path):
+    """config/STC/mocodad_train.yaml has seg_stride 6: the reference drops every trajectory too short for one STRIDED window
+    before fitting (get_robust_data.py:44,58).  Fixture: the unmodified reference's pickle at seg_len 6, seg_stride 3."""
+    import argparse
+    import pickle
+    from mocodad_b200 import MoCoDAD, synthetic as synth
+    from test_module import BASE
+    g = np.load(GOLD)
+    eng = _engine(6)
+    sk = eng.fit_scaler_host(g["train_coords"], g["train_lengths"], g["vid_res"], seg_stride=3)
+    assert np.array_equal(np.asarray(sk.center_, np.float64), g["center_s3"]) and np.array_equal(np.asarray(sk.scale_, np.float64), g["scale_s3"])
+    assert not np.array_equal(g["center_s3"], g["center"])
+    # through the module: the YAML's seg_stride reaches the fit of the 'train' split (and only that split)
+    data_dir, ckpt_dir = tmp_path / "data", tmp_path / "ckpt"
+    ckpt_dir.mkdir()
+    row0 = 0
+    for k, n in enumerate(g["train_lengths"]):
+        folder = data_dir / "training" / "trajectories" / f"01-{k + 1:04d}"
+        folder.mkdir(parents=True)
+        rows = np.concatenate([np.arange(1, n + 1, dtype=np.float64)[:, None], g["train_coords"][row0:row0 + n].astype(np.float64)], axis=1)
+        np.savetxt(folder / "0001.csv", rows, delimiter=",", fmt=["%d"] + ["%.2f"] * 34)
+        row0 += n
+    cfg = dict(BASE, ckpt_dir=str(ckpt_dir), data_dir=str(data_dir), vid_res=[float(v) for v in g["vid_res"]], seg_stride=3, split="train")
+    model = MoCoDAD(argparse.Namespace(**cfg))
+    model.load_state_dict(synth.synth_state_dict(synth.state_dict_spec(T=3, T_cond=3), seed=0))
+    model.to("cuda:0").fit_trajectory_scaler()
+    with open(ckpt_dir / "local_robust.pickle", "rb") as fh:
+        got = pickle.load(fh)
+    assert np.array_equal(np.asarray(got.center_, np.float64), g["center_s3"]) and np.array_equal(np.asarray(got.scale_, np.float64), g["scale_s3"])
+
+
 def test_window_table_equals_the_loop_restatement_on_random_trajectory_sets():
     """Vectorised host table (mocodad_b200/ingest.py) vs the loop restatement of preprocessing.py:55-86, ragged inputs."""
     from hypothesis import given, settings, strategies as st
