@@ -168,7 +168,9 @@ MCD_API int mcd_expand_transforms(const mcd_model* m, const float* d_base, int64
  * (rows were scaled by mcd_normalize_frames).  h_mats [num_transform][6] as for
  * mcd_expand_transforms (NULL = the identity, num_transform must be 1: the base windows).
  * d_win_start [N] int64 on the device; the caller guarantees every window lies inside [0,F).
- * d_out [n_items,2,n_frames,17]. */
+ * d_out [n_items,2,n_frames,17].
+ * The three ingest calls (mcd_expand_transforms, mcd_normalize_frames, mcd_build_items) read only the handle's device and
+ * n_frames: they work on a handle that has no weights yet (before mcd_model_finalize), e.g. a data loader's own handle. */
 MCD_API int mcd_normalize_frames(const mcd_model* m, const float* d_rows, int64_t F, float vid_w, float vid_h,
                          const double* h_center, const double* h_scale, float* d_out, void* stream);
 MCD_API int mcd_build_items(const mcd_model* m, const float* d_rows, int64_t F, const int64_t* d_win_start, int64_t N,

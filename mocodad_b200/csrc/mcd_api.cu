@@ -110,7 +110,7 @@ struct ProfEvent { cudaEvent_t a, b; int slot; int64_t windows; };
 struct mcd_model {
   mcd_config cfg{};
   int T = 0, Tc = 0, t0_corrupt = 0, t0_cond = 0, E = 0, N = 0;
-  int num_sms = 0;
+  mutable int num_sms = 0;
   bool finalized = false;
   std::map<std::string, std::vector<float>> tensors;
   float* d_arena = nullptr;
@@ -750,6 +750,17 @@ int check_ready(const mcd_model* m) {
   return MCD_OK;
 }
 
+// window-ingest entry points need a handle (device, seg_len) but no weights: usable before mcd_model_finalize
+int check_created(const mcd_model* m) {
+  if (m == nullptr) return fail(MCD_ERR_INVALID_ARG, "model handle is NULL");
+  if (m->num_sms == 0) {
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->cfg.device));
+    m->num_sms = sms;
+  }
+  return MCD_OK;
+}
+
 int64_t tile_unit(const mcd_model* m) { return int64_t(m->num_sms) * nw_for(m->T, 17); }
 // default pass size of the virtual batch, in waves of CTA tiles: long enough that the pipeline fill / drain and the
 // launch prologue of the persistent block kernels are ~1 % of a launch (6.9 GB of workspace at T=24)
@@ -1193,7 +1204,7 @@ int mcd_pose_transform_matrix(int32_t index, float* h_mat6) {
 
 int mcd_expand_transforms(const mcd_model* m, const float* d_base, int64_t N, const float* h_mats, int32_t num_transform,
                           int64_t first_item, int64_t n_items, float* d_out, void* stream) {
-  MCD_TRY(check_ready(m));
+  MCD_TRY(check_created(m));
   if (d_base == nullptr || d_out == nullptr || h_mats == nullptr || N < 1 || n_items < 0 || first_item < 0)
     return fail(MCD_ERR_INVALID_ARG, "mcd_expand_transforms: bad argument");
   if (num_transform < 1 || num_transform > kMaxTransforms)
@@ -1233,7 +1244,7 @@ int fill_scaler(const char* who, const double* h_center, const double* h_scale, 
 
 int mcd_normalize_frames(const mcd_model* m, const float* d_rows, int64_t F, float vid_w, float vid_h, const double* h_center,
                          const double* h_scale, float* d_out, void* stream) {
-  MCD_TRY(check_ready(m));
+  MCD_TRY(check_created(m));
   if (F < 0) return fail(MCD_ERR_INVALID_ARG, "mcd_normalize_frames: negative row count");
   if (!(vid_w >= 1.f) || !(vid_h >= 1.f)) return fail(MCD_ERR_INVALID_ARG, "mcd_normalize_frames: video resolution %g x %g", vid_w, vid_h);
   ScalerTable sc{};
@@ -1254,7 +1265,7 @@ int mcd_normalize_frames(const mcd_model* m, const float* d_rows, int64_t F, flo
 int mcd_build_items(const mcd_model* m, const float* d_rows, int64_t F, const int64_t* d_win_start, int64_t N, int32_t row_step,
                     const double* h_center, const double* h_scale, const float* h_mats, int32_t num_transform, int64_t first_item,
                     int64_t n_items, float* d_out, void* stream) {
-  MCD_TRY(check_ready(m));
+  MCD_TRY(check_created(m));
   if (d_rows == nullptr || d_win_start == nullptr || F < 1 || N < 1 || n_items < 0 || first_item < 0 || row_step < 1)
     return fail(MCD_ERR_INVALID_ARG, "mcd_build_items: bad argument");
   if (reinterpret_cast<uintptr_t>(d_rows) & 7) return fail(MCD_ERR_INVALID_ARG, "mcd_build_items: frame rows must be 8-byte aligned");

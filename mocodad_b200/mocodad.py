@@ -30,34 +30,9 @@ from .params import state_dict_spec
 
 try:  # the reference's orchestration layer, when installed
     import pytorch_lightning as _pl
-    _Base = _pl.LightningModule
-except Exception:  # pragma: no cover - Lightning is absent in the build container
-    class _Base(nn.Module):
-        """The slice of LightningModule the scoring path touches (mocodad.py:41-43,230-321)."""
-
-        def __init__(self):
-            super().__init__()
-            self.hparams = argparse.Namespace()
-            self._logged: Dict[str, float] = {}
-
-        @property
-        def device(self) -> torch.device:
-            for p in self.parameters():
-                return p.device
-            return torch.device("cpu")
-
-        def save_hyperparameters(self, args=None, *a, **k) -> None:
-            if args is not None:
-                self.hparams = args
-
-        def log(self, name, value, *a, **k) -> None:
-            self._logged[name] = float(value)
-
-        def on_test_epoch_start(self) -> None:
-            pass
-
-        def on_validation_epoch_start(self) -> None:
-            pass
+except Exception:  # pragma: no cover - Lightning is absent in the build container and on the B200 boxes
+    from .lightning_standin import pytorch_lightning as _pl
+_Base = _pl.LightningModule
 
 
 class _ParamNode(nn.Module):
@@ -465,7 +440,7 @@ class MoCoDAD(_Base):
     def _load_tensors(self, split_name: str, aggr_strategy: str, n_gen: int) -> Dict[str, torch.Tensor]:
         """mocodad.py:583-603"""
         path = os.path.join(self.ckpt_dir, 'saved_tensors_{}_{}_{}'.format(split_name, aggr_strategy, n_gen))
-        return {f.split('.')[0]: torch.load(os.path.join(path, f)) for f in os.listdir(path)}
+        return {f.split('.')[0]: torch.load(os.path.join(path, f), weights_only=False) for f in os.listdir(path)}   # numpy arrays, like upstream
 
     def _save_tensors(self, tensors, split_name: str, aggr_strategy: str, n_gen: int) -> None:
         """mocodad.py:689-705"""
@@ -627,4 +602,4 @@ class MoCoDADlatent(MoCoDAD):
 
     def _freeze_main_net_and_load_ckpt(self) -> None:
         """mocodad_latent.py:222-227"""
-        self.load_state_dict(torch.load(self.pretrained_model_ckpt_path, map_location='cpu')['state_dict'], strict=False)
+        self.load_state_dict(torch.load(self.pretrained_model_ckpt_path, map_location='cpu', weights_only=False)['state_dict'], strict=False)

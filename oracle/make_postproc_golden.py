@@ -26,9 +26,65 @@ CASES = {
 }
 
 
+# HR-UBnormal (config/UBnormal/mocodad_test.yaml: use_hr true): boolean keep-masks per clip, read by the reference from the
+# cwd-relative ./data/UBnormal/hr_bool_masks/{testing,validating}/test_frame_mask/{scene}_{clip}.npy (utils/eval_utils.py:169-185)
+HR_CASES = {
+    # name: (clips, clips that have a mask file, split, pad_size, frames_shift, filter_kernel_size, num_transform)
+    "hr_ubnormal_test": ({(3, 7): 301, (12, 1): 451, (5, 2): 223}, [(3, 7), (12, 1)], "test", -1, 18, 30, 2),
+    "hr_ubnormal_validation": ({(2, 9): 260, (4, 4): 340}, [(4, 4)], "validation", -1, 18, 30, 3),
+}
+
+
+def hr_masks(clips, masked, seed=77):
+    """Seeded boolean keep-masks (about 70 % of the frames kept, in runs) for the clips that have a mask file."""
+    rng = np.random.default_rng(seed)
+    res = {}
+    for key in masked:
+        n = clips[key]
+        keep = np.ones(n, dtype=bool)
+        for _ in range(4):
+            a = int(rng.integers(0, n - 20))
+            keep[a:a + int(rng.integers(10, n // 6))] = False
+        res[key] = keep
+    return res
+
+
+def write_hr_masks(root, split, masks):
+    sub = "testing" if "test" in split else "validating"
+    d = os.path.join(root, "data", "UBnormal", "hr_bool_masks", sub, "test_frame_mask")
+    os.makedirs(d)
+    for (scene, clip), keep in masks.items():
+        np.save(os.path.join(d, f"{scene}_{clip}.npy"), keep)
+
+
 def main():
     MoCoDAD = load_reference()
     rec = {}
+    for name, (clips, masked, split, pad, shift, ksize, ntr) in HR_CASES.items():
+        out, trans, meta, frames, gt = synthetic.synth_scored_dataset(clips, num_transform=ntr, seed=len(name))
+        with tempfile.TemporaryDirectory() as d:
+            gt_dir = os.path.join(d, "gt")
+            os.makedirs(gt_dir)
+            for (scene, clip), g in gt.items():
+                np.save(os.path.join(gt_dir, f"{scene:02d}_{clip:04d}.npy"), g)
+            write_hr_masks(d, split, hr_masks(clips, masked))
+            cwd = os.getcwd()
+            os.chdir(d)
+            try:
+                me = types.SimpleNamespace(gt_path=gt_dir, split=split, use_hr=True, dataset_name="UBnormal", num_transforms=ntr,
+                                           anomaly_score_pad_size=pad, anomaly_score_frames_shift=shift,
+                                           anomaly_score_filter_kernel_size=ksize)
+                ref_auc = MoCoDAD.post_processing(me, out, np.zeros((len(out), 2, 6, 17), np.float32), trans, meta, frames)
+                me.use_hr = False
+                ref_auc_all = MoCoDAD.post_processing(me, out, np.zeros((len(out), 2, 6, 17), np.float32), trans, meta, frames)
+                mine = postproc.dataset_auc(out, trans, meta, frames, postproc.load_ground_truth(gt_dir), num_transform=ntr,
+                                            pad_size=pad, frames_shift=shift, filter_kernel_size=ksize,
+                                            clip_masks=postproc.hr_ubnormal_masks(split))
+            finally:
+                os.chdir(cwd)
+        print(f"[postproc golden] {name}: reference AUC (use_hr) {ref_auc:.12f}  restated {mine:.12f}  (all frames: {ref_auc_all:.12f})")
+        assert abs(ref_auc - mine) < 1e-12 and abs(ref_auc - ref_auc_all) > 1e-6, name
+        rec[name] = np.float64(ref_auc)
     for name, (clips, dataset, pad, shift, ksize, ntr) in CASES.items():
         out, trans, meta, frames, gt = synthetic.synth_scored_dataset(clips, num_transform=ntr)
         with tempfile.TemporaryDirectory() as d:

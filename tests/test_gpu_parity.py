@@ -422,3 +422,33 @@ def test_layer_taps_with_many_tiles_per_cta_vs_oracle(T, n):
         got = eng.unet_tap(x, 6, demb, k, want.shape[1], want.shape[3])
         np.testing.assert_allclose(_np(got), want.numpy(), rtol=0, atol=2e-5, err_msg=f"T={T} {k}")
     np.testing.assert_allclose(_np(eng.unet_forward(x, 6, demb)), eps.numpy(), rtol=0, atol=2e-5)
+
+
+def test_seeded_torch_rng_on_cuda_reproduces_the_eager_reference_draws():
+    """SURVEY.md 8 row a10, "identical inputs and seeds": with `b200_rng: torch` the module draws its noise with torch.randn on
+    the CUDA generator in the reference's call order (mocodad.py:162,176), so under one torch.manual_seed it scores with exactly
+    the noise the reference's randn_like calls would see on this GPU.  Reference arm: the oracle port's ATen operators as CUDA
+    eager (TF32 off -- cuDNN would otherwise round the 1x1 convolutions to 10 mantissa bits), randn_like = torch.randn_like."""
+    import argparse
+    from mocodad_b200 import MoCoDAD
+    from test_module import BASE
+    seg_len, N, G, B = 6, 10, 4, 300
+    sd = synth.synth_state_dict(synth.state_dict_spec(T=3, T_cond=3), seed=0)
+    m = MoCoDAD(argparse.Namespace(**dict(BASE, seg_len=seg_len, noise_steps=N, n_generated_samples=G, b200_rng="torch")))
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    batch = synth.synth_batch(B, seg_len, seed=71)
+    torch.manual_seed(20240607)
+    got = m.forward(batch)[0]
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(20240607)
+        with torch.no_grad():
+            want, _ = ref_port.reverse_diffusion({k: v.to(DEV) for k, v in sd.items()}, batch[0].to(DEV), noise_steps=N,
+                                                 n_generated_samples=G, randn_like=torch.randn_like)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    np.testing.assert_allclose(_np(got), _np(want), rtol=0, atol=1e-4)
+    torch.manual_seed(1)
+    assert not torch.allclose(m.forward(batch)[0], got, atol=1e-3)     # another seed, another noise

@@ -56,3 +56,54 @@ def test_module_post_processing_reads_gt_files(tmp_path, golden):
     m = MoCoDAD(argparse.Namespace(**cfg))
     auc = m.post_processing(out, None, trans, meta, frames)
     assert abs(auc - float(golden("postproc")["avenue_like"])) < 1e-9
+
+
+# ---- HR-UBnormal (use_hr: true, the shipped UBnormal test config): per-clip boolean keep-masks from
+# ./data/UBnormal/hr_bool_masks/{testing,validating}/test_frame_mask (utils/eval_utils.py:169-185, mocodad.py:403-406).
+# Same seeded masks as oracle/make_postproc_golden.py wrote for the unmodified reference.
+HR_CASES = {
+    "hr_ubnormal_test": ({(3, 7): 301, (12, 1): 451, (5, 2): 223}, [(3, 7), (12, 1)], "test", -1, 18, 30, 2),
+    "hr_ubnormal_validation": ({(2, 9): 260, (4, 4): 340}, [(4, 4)], "validation", -1, 18, 30, 3),
+}
+
+
+def _hr_masks(clips, masked, seed=77):
+    rng = np.random.default_rng(seed)
+    res = {}
+    for key in masked:
+        n = clips[key]
+        keep = np.ones(n, dtype=bool)
+        for _ in range(4):
+            a = int(rng.integers(0, n - 20))
+            keep[a:a + int(rng.integers(10, n // 6))] = False
+        res[key] = keep
+    return res
+
+
+@pytest.mark.parametrize("name", list(HR_CASES))
+def test_hr_ubnormal_masks_through_the_module(tmp_path, monkeypatch, golden, name):
+    import argparse
+    from mocodad_b200 import MoCoDAD
+    from test_module import BASE
+    clips, masked, split, pad, shift, ksize, ntr = HR_CASES[name]
+    out, trans, meta, frames, gt = synthetic.synth_scored_dataset(clips, num_transform=ntr, seed=len(name))
+    gt_dir = tmp_path / "gt"
+    gt_dir.mkdir()
+    for (scene, clip), g in gt.items():
+        np.save(gt_dir / f"{scene:02d}_{clip:04d}.npy", g)
+    sub = "testing" if "test" in split else "validating"
+    mdir = tmp_path / "data" / "UBnormal" / "hr_bool_masks" / sub / "test_frame_mask"
+    mdir.mkdir(parents=True)
+    for (scene, clip), keep in _hr_masks(clips, masked).items():
+        np.save(mdir / f"{scene}_{clip}.npy", keep)
+    monkeypatch.chdir(tmp_path)                                    # the reference reads the masks relative to the cwd
+    want = float(golden("postproc")[name])
+    cfg = dict(BASE, gt_path=str(gt_dir), dataset_choice="UBnormal", use_hr=True, split=split, pad_size=pad, frames_shift=shift,
+               filter_kernel_size=ksize, num_transform=ntr)
+    m = MoCoDAD(argparse.Namespace(**cfg))
+    assert abs(m.post_processing(out, None, trans, meta, frames) - want) < 1e-9
+    # the masks matter: without use_hr the AUC is another number
+    m_all = MoCoDAD(argparse.Namespace(**dict(cfg, use_hr=False)))
+    assert abs(m_all.post_processing(out, None, trans, meta, frames) - want) > 1e-6
+    masks = postproc.hr_ubnormal_masks(split)
+    assert sorted(masks) == sorted(masked) and all(v.dtype == bool for v in masks.values())
