@@ -46,6 +46,9 @@ def parse_args():
     p.add_argument("--ref-sample", default="32x5", help="--impl reference: windows x samples per step")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-shipped", action="store_true", help="skip the shipped-shape (T=3, B=1024 / 2048) sub-record")
+    p.add_argument("--stress", action="store_true",
+                   help="BASELINE.json configs[4]-style sweep (e.g. --batch 125000 --noise-steps 1000 --gen 1 on 8 GPUs): device-timed "
+                        "value only, warm-up on 1/32 of the batch, no e2e / baselines / per-kernel profile")
     return p.parse_args()
 
 
@@ -302,6 +305,44 @@ def run_b200(a):
 
     T = a.seg_len - 3
     B = a.batch
+    if a.stress:
+        eng = ScoringEngine(seg_len=a.seg_len, n_frames_cond=3, noise_steps=N, device=dev)
+        eng.load_state_dict(synth.synth_state_dict(synth.state_dict_spec(T=T, T_cond=3), seed=0))
+        data = synth.synth_batch(B, a.seg_len, seed=1 + rank)[0].to(dev)
+        small = data[: max(1, B // 32)].contiguous()
+        for _ in range(max(a.warmup, 1)):
+            eng.reverse_diffusion(small, G, seed=999, first_window=rank * B)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = eng.launch_count()
+        with ClockSampler(local) as clocks:
+            barrier()
+            ev0.record()
+            for k in range(a.steps):
+                best = eng.reverse_diffusion(data, G, seed=999, first_window=(k * world + rank) * B)["best"]
+                if world > 1:
+                    best = gather_scores(best, world * B)
+            ev1.record()
+            barrier()
+        ms = max_over_ranks(ev0.elapsed_time(ev1)) / a.steps
+        assert bool(torch.isfinite(best).all())
+        if rank == 0:
+            value = world * B / (ms * 1e-3)
+            bytes_ws = {3: 230952.0, 24: 1847616.0}.get(T)
+            peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            hbm_peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+            line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 1),
+                    "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": dict(workload_config(a), stress=True, total_windows=world * B,
+                                   warmup_note="warm-up steps score 1/32 of the batch (same kernels)"),
+                    "window_steps_per_sec": value * G * (N - 1), "gpu_launches": eng.launch_count() - l0, "clocks": clocks.summary(),
+                    "whole_step_hbm": None if bytes_ws is None else {
+                        "achieved_per_gpu": round(bytes_ws * value * G * (N - 1) / world / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
+                        "frac": round(bytes_ws * value * G * (N - 1) / world / 1e9 / hbm_peak, 4)}}
+            _emit(out_fd, line)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     main = measure(a.seg_len, B, a.steps, a.warmup, True)
     eng, host, data, ms, value, e2e_s, e2e_value = (main[k] for k in ("eng", "host", "data", "ms", "value", "e2e_s", "e2e_value"))
     launches, clocks_summary, step_device = main["launches"], main["clocks"], main["step_device"]

@@ -221,6 +221,36 @@ int block_op(int action, const mcd_model* m, int slot, const BlockWeights* w, co
   return launch_block<Cfg>(m, slot, *w, *io, s);
 }
 
+// Tiled-TMA view of a planar-4 activation tensor [n][C/4][P = T*V][4] for the multi-window tiles of the tensor-core block:
+// dims (fastest first) [4V floats of a frame | T frames | C/4 planes | n windows]; box [4V, T, 1, NW] = one 4-channel plane of
+// NW consecutive windows, landing as [window][position] 16-byte elements -- one plane of the kernel's planar X buffer.
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<TensorMapEncodeFn>(p);
+  }();
+  return fn;
+}
+int make_x_tensor_map(CUtensorMap* map, const float* base, int64_t n, int C, int T, int V, int NW) {
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (enc == nullptr) return fail(MCD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t P = cuuint64_t(T) * V;
+  const cuuint64_t gdim[4] = {cuuint64_t(4 * V), cuuint64_t(T), cuuint64_t(C / 4), cuuint64_t(n)};
+  const cuuint64_t gstride[3] = {cuuint64_t(V) * 16, P * 16, cuuint64_t(C / 4) * P * 16};   // bytes, dims 1..3
+  const cuuint32_t box[4] = {cuuint32_t(4 * V), cuuint32_t(T), 1u, cuuint32_t(NW)};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return fail(MCD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (C=%d T=%d V=%d n=%lld)", int(rc), C, T, V, (long long)n);
+  return MCD_OK;
+}
+
 // The dense middle blocks: 1x1 channel contraction on the tensor cores (mcd_block_tc.cuh).
 template <int T, int V, int CIN, int COUT>
 int dense_block_op(int action, const mcd_model* m, int slot, const BlockWeights* w, const BlockIO* io, cudaStream_t s) {
@@ -236,9 +266,12 @@ int dense_block_op(int action, const mcd_model* m, int slot, const BlockWeights*
   const int grid = int(ntiles < m->num_sms ? ntiles : m->num_sms);
   BlockIO io2 = *io;
   if (m->d_trace != nullptr && m->trace_slot == slot) { io2.trace = m->d_trace; io2.trace_cap = m->trace_cap; m->trace_slot = -1; }
+  alignas(64) CUtensorMap tmx;
+  memset(&tmx, 0, sizeof(tmx));
+  if (Tc::TMA_TILED) MCD_TRY(make_x_tensor_map(&tmx, io->in, io->n, CIN, T, V, Tc::NW));
   {
     LaunchScope ls(m, slot, io->n, s);
-    stgcn_block_tc_kernel<Tc><<<grid, kTcThreads, Tc::SMEM_BYTES, s>>>(*w, io2);
+    stgcn_block_tc_kernel<Tc><<<grid, kTcThreads, Tc::SMEM_BYTES, s>>>(*w, io2, tmx);
   }
   return check_launch(kSlotNames[slot]);
 }
@@ -635,7 +668,7 @@ bool bn_fold(const mcd_model* m, const std::string& p, int C, std::vector<double
 struct BlockOffsets { size_t A, Tm, TmE, W, Wr, bias, WE, bE, Bop; bool has_bop; };
 
 bool pack_block(const mcd_model* m, Arena* ar, const std::string& p, int cin, int cout, int T, int V, bool emb, int E,
-                PackedBlock* pb, BlockOffsets* off, std::string* missing) {
+                PackedBlock* pb, BlockOffsets* off, std::string* missing, bool tc_block = false) {
   const int VP = (V + 3) / 4 * 4, TP4 = (T + 3) / 4 * 4, TMS = T * TP4 + 4;
   const int cinp = cin < 4 ? 4 : cin;
   pb->cin = cin; pb->cout = cout; pb->V = V; pb->T = T; pb->emb = emb; pb->resconv = cin != cout;
@@ -699,7 +732,9 @@ bool pack_block(const mcd_model* m, Arena* ar, const std::string& p, int cin, in
   off->has_bop = (cin % 16 == 0) && (cout % 32 == 0);
   off->Bop = 0;
   if (off->has_bop) {
-    const int nparts = pb->resconv ? 4 : 2;
+    // TcCfg::IDRES_MMA: identity-residual blocks of short windows carry the identity as residual-convolution operand
+    const bool id_conv = tc_block && !pb->resconv && T <= 4 && V <= 12;
+    const int nparts = (pb->resconv || id_conv) ? 4 : 2;
     const size_t wch = size_t(nparts) * cout * 16;
     off->Bop = ar->alloc(wch * (cin / 16));
     auto lo_part = [](float w) {
@@ -721,6 +756,8 @@ bool pack_block(const mcd_model* m, Arena* ar, const std::string& p, int cin, in
           const float wr = ar->h[off->Wr + size_t(k) * cout + co];
           ar->h[off->Bop + c * wch + 2 * size_t(cout) * 16 + pos] = wr;
           ar->h[off->Bop + c * wch + 3 * size_t(cout) * 16 + pos] = lo_part(wr);
+        } else if (id_conv) {
+          ar->h[off->Bop + c * wch + 2 * size_t(cout) * 16 + pos] = k == co ? 1.0f : 0.0f;   // hi part of I; its lo part is zero
         }
       }
   }
@@ -942,7 +979,7 @@ int mcd_model_finalize(mcd_model* m) {
   for (int i = 0; i < m->n_blocks; ++i) {
     const BlockShape& b = kUnetBlocks[i];
     ok = pack_block(m, &ar, std::string("model.") + b.name + ".", b.cin, b.cout, m->T, kPyramid[b.level], true, m->E, &m->unet[i],
-                    &uo[i], &missing) && ok;
+                    &uo[i], &missing, true) && ok;
   }
   size_t rsW[kNumResample] = {}, rsb[kNumResample] = {};
   for (int i = 0; i < m->n_rs; ++i) {

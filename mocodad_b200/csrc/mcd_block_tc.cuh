@@ -32,6 +32,7 @@
 //               two accumulator sets).
 // T-mix of chunk c+1, A-mix of chunk c, the MMAs of chunk c-1 and the epilogue of the previous tile overlap.
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include "mcd_kernels.cuh"
 
 #ifndef MCD_TC_TRACE
@@ -120,6 +121,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                "r"(bytes), "r"(bar)
+               : "memory");
+}
+// TMA tiled copy (cp.async.bulk.tensor, SASS UTMALDG) of one 4-D box; out-of-range coordinates are zero-filled and the
+// whole box is counted on the mbarrier
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
                : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -235,8 +243,18 @@ struct TcCfg {
   static constexpr int KC = 16;
   static constexpr int NCHUNK = CIN / KC;
   static constexpr int C4 = KC / 4;
-  static constexpr bool RESCONV = CIN != COUT;
+  // Identity residual through the tensor pipe (short windows, narrow levels): the block is run as if it had a residual
+  // convolution whose weight is the identity (X_hi*I + X_lo*I = X exactly).  The epilogue then never re-reads X from global
+  // memory -- at T=3 those loads were 40 % of the epilogue warps' stall samples (profiles/r02_ncu_T3_summary.txt) -- at the
+  // price of tensor-pipe reads of X / Xlo, which these blocks have room for (shared memory 30 % busy).  Kept off where the
+  // extra Xlo buffer would cost the second Y2 buffer (V=17) and at long windows (shared-memory bound).
+  static constexpr bool IDRES_MMA = CIN == COUT && T <= 4 && V <= 12;
+  static constexpr bool RESCONV = CIN != COUT || IDRES_MMA;
   static constexpr int NPART = RESCONV ? 4 : 2;  // weight operand parts per chunk: W hi, W lo [, Wr hi, Wr lo]
+  // Multi-window tiles (T <= 12) are loaded with ONE tiled TMA copy per 4-channel plane (box = [frame row, T, 1 plane, NW
+  // windows]) instead of one bulk copy per (window, plane): at T=3 the 32 small copies per chunk cost the loader warp ~3 k
+  // cycles of issue and made it the bottleneck of the V=12 / V=10 blocks (profiles/r02_waits_T3.log)
+  static constexpr bool TMA_TILED = NW > 1;
   static constexpr bool RES_AHEAD = true;        // residual MMAs one chunk ahead of the convolution MMAs (see the MMA warp)
   static constexpr int VP = (V + 3) / 4 * 4;
   static constexpr int TP4 = (T + 3) / 4 * 4;
@@ -320,7 +338,8 @@ enum TcBar {
 };
 
 template <class Cfg>
-__global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const BlockWeights wt, const BlockIO io) {
+__global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const BlockWeights wt, const BlockIO io,
+                                                                       const __grid_constant__ CUtensorMap tmx) {
   constexpr int T = Cfg::T, V = Cfg::V, P = Cfg::P, ROWS = Cfg::ROWS, C4 = Cfg::C4, MT = Cfg::MT;
   constexpr int CIN = Cfg::CIN, COUT = Cfg::COUT, NCHUNK = Cfg::NCHUNK, NW = Cfg::NW, NXB = Cfg::NXB;
   constexpr int VP = Cfg::VP, TP4 = Cfg::TP4, TMS = Cfg::TMS, ARR = Cfg::ARR, WCH = Cfg::WCH;
@@ -694,15 +713,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       // 4-channel plane, which makes the buffer a valid no-swizzle K-major UMMA operand as it stands); windows past
       // the end of the tensor are skipped (their rows are never stored).
       // The copies are issued by different lanes (a single lane needed ~1-2.6 k cycles for the 4*NW issues).
-      int64_t nvalid = io.n - tile * NW;
-      if (nvalid > NW) nvalid = NW;
       constexpr uint32_t PLANE = P * 16;
-      if (lane == 0) mbar_expect_tx(BAR(BAR_X_FULL + b), uint32_t(nvalid) * 4u * PLANE);
-      __syncwarp();
       const uint32_t dst0 = smem_u32(sX + b * ARR);
-      for (int k = lane; k < int(nvalid) * 4; k += 32) {
-        const int wl = k >> 2, j = k & 3;
-        bulk_g2s(dst0 + uint32_t(j * NW + wl) * PLANE, io.in + act_off(tile * NW + wl, chunk * C4 + j, 0, CIN, P), PLANE, BAR(BAR_X_FULL + b));
+      if constexpr (Cfg::TMA_TILED) {
+        // tensor [4V floats | T | CIN/4 planes | n windows] (mcd_api.cu: make_x_tensor_map); windows past the end arrive as zeros
+        if (lane == 0) mbar_expect_tx(BAR(BAR_X_FULL + b), uint32_t(NW) * 4u * PLANE);
+        __syncwarp();
+        if (lane < 4)
+          tma_load_4d(dst0 + uint32_t(lane * NW) * PLANE, &tmx, 0, 0, chunk * C4 + lane, int(tile * NW), BAR(BAR_X_FULL + b));
+      } else {
+        int64_t nvalid = io.n - tile * NW;
+        if (nvalid > NW) nvalid = NW;
+        if (lane == 0) mbar_expect_tx(BAR(BAR_X_FULL + b), uint32_t(nvalid) * 4u * PLANE);
+        __syncwarp();
+        for (int k = lane; k < int(nvalid) * 4; k += 32) {
+          const int wl = k >> 2, j = k & 3;
+          bulk_g2s(dst0 + uint32_t(j * NW + wl) * PLANE, io.in + act_off(tile * NW + wl, chunk * C4 + j, 0, CIN, P), PLANE, BAR(BAR_X_FULL + b));
+        }
       }
       TRACE(3, it, 2);
       __syncwarp();
