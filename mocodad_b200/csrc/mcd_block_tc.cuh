@@ -304,9 +304,23 @@ struct TcCfg {
   // iterations instead of one; the widest tiles (V=17 with a residual convolution) fall back to single Xlo / Y2 buffers.
   static constexpr int SM_MISC = 2 * Y1ARR + 2 * WCH + COUT + NW * COUT;
   static constexpr bool tc_fits(int arrays) { return size_t(SM_MISC + arrays * ARR) * sizeof(float) + 1024 <= 227 * 1024; }
-  static constexpr int NXLO = !RESCONV ? 0 : (tc_fits(2 + 2 + 4) ? 2 : 1);
-  static constexpr int NY2 = tc_fits(2 + NXLO + 4) ? 2 : 1;
-  static constexpr int NXB = tc_fits(3 + NXLO + 2 * NY2) ? 3 : 2;
+  // One-window tiles (T=24): Xlo / Y2 double buffers first, then the third X slot (tuned on the T=24 wait accounting).
+  // Multi-window tiles (short windows): the X ring first -- a chunk is little work there, and with the tiled TMA loader the
+  // round trip "slot released -> copy issued -> data landed" (~2-3 k cycles) is what the T-mix warps wait for (they sat 50-60 %
+  // in x_full with a 2-deep ring while the loader idled, profiles/r02_waits_T3.log); up to 4 slots, Xlo single-buffered.
+  static constexpr int tc_budget() { int a = 0; while (a < 16 && tc_fits(a + 1)) ++a; return a; }
+  static constexpr int BUDGET = tc_budget();
+  static constexpr bool DEEP_X = NW > 1;
+  static constexpr int NXLO0 = !RESCONV ? 0 : (tc_fits(2 + 2 + 4) ? 2 : 1);
+  static constexpr int NY2_0 = tc_fits(2 + NXLO0 + 4) ? 2 : 1;
+  static constexpr int NXB0 = tc_fits(3 + NXLO0 + 2 * NY2_0) ? 3 : 2;
+  static constexpr int NY2_D = BUDGET >= 2 + (RESCONV ? 1 : 0) + 4 ? 2 : 1;
+  static constexpr int NXB_D0 = BUDGET - (RESCONV ? 1 : 0) - 2 * NY2_D;
+  static constexpr int NXB_D = NXB_D0 > 4 ? 4 : (NXB_D0 < 2 ? 2 : NXB_D0);
+  static constexpr int NXLO_D = !RESCONV ? 0 : (BUDGET - NXB_D - 2 * NY2_D >= 2 ? 2 : 1);
+  static constexpr int NXLO = DEEP_X ? NXLO_D : NXLO0;
+  static constexpr int NY2 = DEEP_X ? NY2_D : NY2_0;
+  static constexpr int NXB = DEEP_X ? NXB_D : NXB0;
   static_assert(tc_fits(NXB + NXLO + 2 * NY2), "tensor-core block tile exceeds shared memory");
   static constexpr int SM_X = 0;                 // NXB buffers
   static constexpr int SM_Y1 = SM_X + NXB * ARR;  // 2
@@ -323,19 +337,20 @@ struct TcCfg {
 
 // barrier slots in shared memory
 enum TcBar {
-  BAR_X_FULL = 0,                 // [3] loader -> T-warps (and A-warps / MMA with a residual convolution)
-  BAR_X_EMPTY = 3,                // [3] consumers -> loader
-  BAR_W_FULL = 6,                 // [2] loader (bulk copy) -> MMA warp
-  BAR_Y1_FULL = 8,                // [2] T-warps -> A-warps
-  BAR_Y1_EMPTY = 10,              // [2] A-warps -> T-warps
-  BAR_OPS_FULL = 12,              // [2] A-warps -> MMA warp
-  BAR_MMA_DONE = 14,              // [2] tcgen05.commit -> A-warps, loader (operand buffers free)
-  BAR_ACC_FULL = 16,              // [2] tcgen05.commit -> epilogue
-  BAR_ACC_EMPTY = 18,             // [2] epilogue -> MMA warp
-  BAR_XLO_FULL = 20,              // [2] conversion warp -> MMA warp (residual convolution)
-  BAR_RES_DONE = 22,              // [2] tcgen05.commit -> conversion warp (Xlo buffer free)
-  BAR_COUNT = 24
+  BAR_X_FULL = 0,                 // [4] loader -> T-warps (and A-warps / MMA with a residual convolution)
+  BAR_X_EMPTY = 4,                // [4] consumers -> loader
+  BAR_W_FULL = 8,                 // [2] loader (bulk copy) -> MMA warp
+  BAR_Y1_FULL = 10,               // [2] T-warps -> A-warps
+  BAR_Y1_EMPTY = 12,              // [2] A-warps -> T-warps
+  BAR_OPS_FULL = 14,              // [2] A-warps -> MMA warp
+  BAR_MMA_DONE = 16,              // [2] tcgen05.commit -> A-warps, loader (operand buffers free)
+  BAR_ACC_FULL = 18,              // [2] tcgen05.commit -> epilogue
+  BAR_ACC_EMPTY = 20,             // [2] epilogue -> MMA warp
+  BAR_XLO_FULL = 22,              // [2] conversion warp -> MMA warp (residual convolution)
+  BAR_RES_DONE = 24,              // [2] tcgen05.commit -> conversion warp (Xlo buffer free)
+  BAR_COUNT = 26
 };
+constexpr int kTcMaxXSlots = 4;
 
 template <class Cfg>
 __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const BlockWeights wt, const BlockIO io,
@@ -420,7 +435,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   } else if (tid == 0) {
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < kTcMaxXSlots; ++i) {
       mbar_init(BAR(BAR_X_FULL + i), 1);  // one expect_tx arrival + the bulk copies' bytes
       mbar_init(BAR(BAR_X_EMPTY + i), RESCONV ? kTcMix + 1 : kTcMix);  // T-warps (+ the commit of the residual MMAs)
     }
