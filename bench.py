@@ -228,8 +228,9 @@ def run_b200(a):
     out_fd = None
     if world > 1:
         # NCCL's communicator lines must reach the driver (it checks the rank count); they go to stderr, the JSON line alone to stdout
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE") and not os.environ.get("MCD_QUIET_NCCL"):
+            os.environ["NCCL_DEBUG"] = "INFO"          # boxes export VERSION by default: the communicator lines need INFO
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         out_fd = _stdout_to_stderr()
         dist.init_process_group("nccl", device_id=dev)
 
