@@ -247,7 +247,8 @@ struct TcCfg {
   // convolution whose weight is the identity (X_hi*I + X_lo*I = X exactly).  The epilogue then never re-reads X from global
   // memory -- at T=3 those loads were 40 % of the epilogue warps' stall samples (profiles/r02_ncu_T3_summary.txt) -- at the
   // price of tensor-pipe reads of X / Xlo, which these blocks have room for (shared memory 30 % busy).  Kept off where the
-  // extra Xlo buffer would cost the second Y2 buffer (V=17) and at long windows (shared-memory bound).
+  // extra Xlo buffer would cost the second Y2 buffer (V=17) and at long windows (measured at T=24, V=12: no change -- the T-mix
+  // warps, not the epilogue, are the critical role there).
   static constexpr bool IDRES_MMA = CIN == COUT && T <= 4 && V <= 12;
   static constexpr bool RESCONV = CIN != COUT || IDRES_MMA;
   static constexpr int NPART = RESCONV ? 4 : 2;  // weight operand parts per chunk: W hi, W lo [, Wr hi, Wr lo]
