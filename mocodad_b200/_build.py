@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB_PATH = os.path.join(PKG, "libmocodad_b200.so")
 STAMP = LIB_PATH + ".stamp"
 SOURCES = ("mcd_api.cu",)
-HEADERS = ("mcd_kernels.cuh", "mcd_block_tc.cuh", "mcd_edge_blocks.cuh", "mcd_latent.cuh",
+HEADERS = ("mcd_kernels.cuh", "mcd_block_tc.cuh", "mcd_block_cf.cuh", "mcd_edge_blocks.cuh", "mcd_latent.cuh",
            os.path.join(ROOT, "include", "mocodad_b200.h"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
@@ -59,6 +59,19 @@ def build_trace_variant() -> str:
     return TRACE_LIB_PATH
 
 
+def build_variant(tag: str, defines) -> str:
+    """Experiment build ``libmocodad_b200_<tag>.so`` with extra ``-D`` flags (A/B runs on one GPU box through
+    ``MOCODAD_B200_LIB``).  Never loaded by default."""
+    out = os.path.join(PKG, f"libmocodad_b200_{tag}.so")
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-Xptxas", "-v"] + [f"-D{d}" for d in defines] + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    with open(out + ".ptxas.log", "w") as fh:
+        fh.write(res.stderr)
+    return out
+
+
 def build_extension(force: bool = False, verbose: bool = False) -> str:
     """Compile the library if sources changed (or ``force``).  Returns the .so path."""
     if not force and is_current():
@@ -77,7 +90,10 @@ def build_extension(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     import sys
-    if "--trace" in sys.argv:
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    elif "--trace" in sys.argv:
         print(build_trace_variant())
     else:
         print(build_extension(force="--force" in sys.argv, verbose="-v" in sys.argv))

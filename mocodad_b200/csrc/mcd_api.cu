@@ -6,6 +6,7 @@
 #include "../../include/mocodad_b200.h"
 #include "mcd_kernels.cuh"
 #include "mcd_block_tc.cuh"
+#include "mcd_block_cf.cuh"
 #include "mcd_edge_blocks.cuh"
 #include "mcd_latent.cuh"
 
@@ -17,6 +18,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 using namespace mcd;
@@ -251,13 +253,24 @@ int make_x_tensor_map(CUtensorMap* map, const float* base, int64_t n, int C, int
   return MCD_OK;
 }
 
-// The dense middle blocks: 1x1 channel contraction on the tensor cores (mcd_block_tc.cuh).
+#ifndef MCD_CONV_FIRST
+#define MCD_CONV_FIRST 1
+#endif
+constexpr bool kConvFirst = MCD_CONV_FIRST != 0;
+
+// The dense middle blocks: 1x1 channel contraction on the tensor cores.  Blocks that keep or widen the channel count mix
+// first (mcd_block_tc.cuh); blocks that narrow it (Cin > Cout) convolve first and mix on the Cout side (mcd_block_cf.cuh).
 template <int T, int V, int CIN, int COUT>
 int dense_block_op(int action, const mcd_model* m, int slot, const BlockWeights* w, const BlockIO* io, cudaStream_t s) {
-  using Tc = TcCfg<T, V, CIN, COUT, nw_for(T, 17)>;
+  constexpr bool CONV_FIRST = kConvFirst && CIN > COUT;
+  using Tc = std::conditional_t<CONV_FIRST, CfCfg<T, V, CONV_FIRST ? CIN : 2 * COUT, COUT, nw_for(T, 17)>, TcCfg<T, V, CIN, COUT, nw_for(T, 17)>>;
   static_assert(Tc::SMEM_BYTES <= 227 * 1024, "tensor-core block kernel exceeds the 227 KB shared memory of an sm_100 CTA");
+  auto kernel = [] {
+    if constexpr (CONV_FIRST) return stgcn_block_cf_kernel<Tc>;
+    else return stgcn_block_tc_kernel<Tc>;
+  }();
   if (action == 0) {
-    CUDA_TRY(cudaFuncSetAttribute(stgcn_block_tc_kernel<Tc>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Tc::SMEM_BYTES)));
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Tc::SMEM_BYTES)));
     return MCD_OK;
   }
   if (w->Bop == nullptr) return fail(MCD_ERR_UNSUPPORTED, "block %s was not packed for the tensor-core kernel", kSlotNames[slot]);
@@ -271,7 +284,7 @@ int dense_block_op(int action, const mcd_model* m, int slot, const BlockWeights*
   if (Tc::TMA_TILED) MCD_TRY(make_x_tensor_map(&tmx, io->in, io->n, CIN, T, V, Tc::NW));
   {
     LaunchScope ls(m, slot, io->n, s);
-    stgcn_block_tc_kernel<Tc><<<grid, kTcThreads, Tc::SMEM_BYTES, s>>>(*w, io2, tmx);
+    kernel<<<grid, kTcThreads, Tc::SMEM_BYTES, s>>>(*w, io2, tmx);
   }
   return check_launch(kSlotNames[slot]);
 }
@@ -734,6 +747,10 @@ bool pack_block(const mcd_model* m, Arena* ar, const std::string& p, int cin, in
   if (off->has_bop) {
     // TcCfg::IDRES_MMA: identity-residual blocks of short windows carry the identity as residual-convolution operand
     const bool id_conv = tc_block && !pb->resconv && T <= 4 && V <= 12;
+    // conv-first blocks (mcd_block_cf.cuh, Cin > Cout): parts ordered [W hi | Wr hi | W lo | Wr lo], so that one N = 2*COUT MMA
+    // forms the convolution and the residual convolution from a single read of the activation operand
+    const bool cf = tc_block && kConvFirst && cin > cout;
+    const int pW_lo = cf ? 2 : 1, pWr_hi = cf ? 1 : 2;
     const int nparts = (pb->resconv || id_conv) ? 4 : 2;
     const size_t wch = size_t(nparts) * cout * 16;
     off->Bop = ar->alloc(wch * (cin / 16));
@@ -751,10 +768,10 @@ bool pack_block(const mcd_model* m, Arena* ar, const std::string& p, int cin, in
         const size_t pos = size_t(co) * 16 + size_t((((kk >> 2) ^ ((co >> 1) & 3)) << 2) + (kk & 3));
         const float w = ar->h[off->W + size_t(k) * cout + co];
         ar->h[off->Bop + c * wch + 0 * size_t(cout) * 16 + pos] = w;
-        ar->h[off->Bop + c * wch + 1 * size_t(cout) * 16 + pos] = lo_part(w);
+        ar->h[off->Bop + c * wch + pW_lo * size_t(cout) * 16 + pos] = lo_part(w);
         if (pb->resconv) {
           const float wr = ar->h[off->Wr + size_t(k) * cout + co];
-          ar->h[off->Bop + c * wch + 2 * size_t(cout) * 16 + pos] = wr;
+          ar->h[off->Bop + c * wch + pWr_hi * size_t(cout) * 16 + pos] = wr;
           ar->h[off->Bop + c * wch + 3 * size_t(cout) * 16 + pos] = lo_part(wr);
         } else if (id_conv) {
           ar->h[off->Bop + c * wch + 2 * size_t(cout) * 16 + pos] = k == co ? 1.0f : 0.0f;   // hi part of I; its lo part is zero

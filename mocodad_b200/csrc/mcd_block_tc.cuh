@@ -263,7 +263,12 @@ struct TcCfg {
   // T-mix: thread = (window slot, joint v, group of QG output frames);  A-mix: thread = (window slot, frame t, WGS joints)
   //        (one-window tiles additionally split the chunk's four 4-channel groups over CS thread sets, tc_pick_shape)
   static constexpr bool SHAPED = NW == 1 && T > 4;
-  static constexpr TcShape SH_T = tc_pick_shape(V, T, T, 100, 8, C4), SH_A = tc_pick_shape(T, V, V, 76, 5, C4);
+  // V=12, T=24: groups of 6 output frames x 2 channel splits (144 weights per thread, no spills under the 200-register
+  // budget) instead of the model's 3 x 1: the same FMA count on the busiest sub-partition and half the X re-reads (each X
+  // element is read by T/QG threads) -- the V=12 blocks run 3-4 % faster (round 2, gpurun e1: 27.1 -> 26.1 ms per 27 launches
+  // of the 64->64 blocks); groups of 5 x 2, which the model rates equal, measured in between
+  static constexpr TcShape SH_T = (V == 12 && T == 24) ? TcShape{6, 2} : tc_pick_shape(V, T, T, 100, 8, C4),
+                           SH_A = tc_pick_shape(T, V, V, 76, 5, C4);
   // (A-mix groups of 6 joints at V=12 measured slower: two joint groups per frame make the operand stores conflict)
   static constexpr int QG = T <= 4 ? T : (SHAPED ? SH_T.g : tc_pick_group(V, T, NW));
   static constexpr int CS_T = SHAPED ? SH_T.cs : 1;
@@ -495,7 +500,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
             float2 a[2][QG];
 #pragma unroll
             for (int q = 0; q < QG; ++q) a[0][q] = a[1][q] = make_float2(0.f, 0.f);
-            constexpr int TB = T % 6 == 0 ? 6 : (T % 3 == 0 ? 3 : (T % 2 == 0 ? 2 : 1));
+            constexpr int TB = QG > 4 ? (T % 3 == 0 ? 3 : 2) : (T % 6 == 0 ? 6 : (T % 3 == 0 ? 3 : (T % 2 == 0 ? 2 : 1)));
             const float* xp = sXc + ((c4 * NW + wl) * P + v) * 4;  // planar X: [c4][window][position] 16-byte elements
             float4 xc[TB], xn[TB];
 #pragma unroll
