@@ -28,21 +28,6 @@
 
 namespace mcd {
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait16(uint32_t* r) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
-                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :
-               : "memory");
-}
-
 template <int T_, int V_, int CIN_, int COUT_, int NW_>
 struct CfCfg {
   using Mix = TcCfg<T_, V_, COUT_, COUT_, NW_>;  // task shapes of the two mixes (they depend on T, V and the window count only)
@@ -93,13 +78,12 @@ enum CfBar {
   CF_XLO_EMPTY = 14, // [2] tcgen05.commit -> conversion warp
   CF_ACC_FULL = 16,  // [2] tcgen05.commit -> drain
   CF_ACC_EMPTY = 18, // [2] final stage -> MMA warp
-  CF_Z_FULL = 20,    // [4] drain -> T-mix (slot = output-chunk iteration % NZ)
-  CF_Z_EMPTY = 24,   // [4] T-mix -> drain
-  CF_Y1_FULL = 28,   // [2] T-mix -> A-mix
-  CF_Y1_EMPTY = 30,  // [2] A-mix -> T-mix
-  CF_Y2_FULL = 32,   // [2] A-mix -> final stage
-  CF_Y2_EMPTY = 34,  // [2] final stage -> A-mix
-  CF_BAR_COUNT = 36
+  CF_Z_FULL = 20,    // [2] drain -> T-mix (slot = output-chunk iteration % NZ); no "Z empty" barrier: see the drain
+  CF_Y1_FULL = 22,   // [2] T-mix -> A-mix
+  CF_Y1_EMPTY = 24,  // [2] A-mix -> T-mix
+  CF_Y2_FULL = 26,   // [2] A-mix -> final stage
+  CF_Y2_EMPTY = 28,  // [2] final stage -> A-mix
+  CF_BAR_COUNT = 30
 };
 
 template <class Cfg>
@@ -143,10 +127,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_cf_kernel(const Blo
     for (int i = 0; i < 4; ++i) {
       mbar_init(BAR(CF_X_FULL + i), 1);   // one expect_tx arrival + the copies' bytes
       mbar_init(BAR(CF_X_EMPTY + i), 1);  // the commit of the chunk's MMAs
-      mbar_init(BAR(CF_Z_FULL + i), kTcEpilogue);
-      mbar_init(BAR(CF_Z_EMPTY + i), kTcMix);
     }
+    static_assert(Cfg::NZ == 2, "two Z ring barriers");
     for (int i = 0; i < 2; ++i) {
+      mbar_init(BAR(CF_Z_FULL + i), kTcEpilogue);
       mbar_init(BAR(CF_W_FULL + i), 1);
       mbar_init(BAR(CF_W_EMPTY + i), 1);
       mbar_init(BAR(CF_XLO_FULL + i), 32);
@@ -228,8 +212,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_cf_kernel(const Blo
           }
         }
       }
-      mbar_arrive(BAR(CF_Y1_FULL + s));
-      mbar_arrive(BAR(CF_Z_EMPTY + zs));
+      mbar_arrive(BAR(CF_Y1_FULL + s));  // (also releases Z slot zs: the drain refills it only after the final stage of `it`)
     }
   } else if (warp < 8) {
     // =============================== A-mix warps ===============================
@@ -432,7 +415,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_cf_kernel(const Blo
         mbar_wait(BAR(CF_ACC_FULL + set), uint32_t((ti / 2) & 1));
         tc_fence_after();
       }
-      if (d >= Cfg::NZ) mbar_wait(BAR(CF_Z_EMPTY + zs), uint32_t((d / Cfg::NZ - 1) & 1));  // the T-mix warps are done with the slot
+      // Slot zs is free without a barrier of its own: drain(d) runs after final_stage(d - NZ), which waited for Y2_FULL of that
+      // iteration (A-mix done), whose A-mix waited for Y1_FULL (arrived by every T-mix thread AFTER its last read of the slot)
       float* zc = sZ + zs * ARR;
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
@@ -456,6 +440,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_cf_kernel(const Blo
       const int64_t tile = blockIdx.x + int64_t(ti) * gridDim.x;
       mbar_wait(BAR(CF_Y2_FULL + s), uint32_t((it / 2) & 1));
       const float* y2 = sY2 + s * ARR;
+      // the chunk's bias (and, for one-window tiles, its embedding values) are the same for every row: read once per chunk
+      constexpr bool EMB_HOIST = NW == 1;
+      const float4* bp = reinterpret_cast<const float4*>(sBias + c * 16);
+      float4 b4[4] = {bp[0], bp[1], bp[2], bp[3]}, e4[4];
+      if constexpr (EMB_HOIST) {
+        const float4* ep = reinterpret_cast<const float4*>(sEmb + c * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) e4[j] = ep[j];
+      }
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
         const int r = m * 128 + q * 32 + lane;
@@ -466,14 +459,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_cf_kernel(const Blo
         uint32_t acc[16];
         tmem_ld16(tmem + (uint32_t(q * 32) << 16) + uint32_t(set * Cfg::ACC_COLS + m * Cfg::TCOLS + COUT + c * 16), acc);
         const int rr = ok ? r : 0;
-        float4 y[4], b4[4], e4[4];
-        const float4* bp = reinterpret_cast<const float4*>(sBias + c * 16);
-        const float4* ep = reinterpret_cast<const float4*>(sEmb + (ok ? wl : 0) * COUT + c * 16);
+        float4 y[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          y[j] = *reinterpret_cast<const float4*>(y2 + (j * ROWS + rr) * 4);
-          b4[j] = bp[j];
-          e4[j] = ep[j];
+        for (int j = 0; j < 4; ++j) y[j] = *reinterpret_cast<const float4*>(y2 + (j * ROWS + rr) * 4);
+        if constexpr (!EMB_HOIST) {
+          const float4* ep = reinterpret_cast<const float4*>(sEmb + (ok ? wl : 0) * COUT + c * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) e4[j] = ep[j];
         }
         float* op = io.out + (ok ? act_off(w, c * 4, pp, COUT, P) : 0);
         tmem_ld_wait16(acc);
@@ -509,8 +501,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_cf_kernel(const Blo
         if (it + NCH2 < npairs2) load_emb(tile + gridDim.x);
       }
       final_stage(it);
-      // refill the Z slot this chunk's mixes released (the A-mix of `it` is done, hence its T-mix) -- possibly with the first
-      // chunks of the next tile, whose convolution ran on the tensor pipe meanwhile
+      // refill the Z slot this chunk's mixes released (the A-mix of `it` is done, hence its T-mix; NZ = 2 = the Y2 ring depth, so
+      // slot (it + NZ) % NZ is the one iteration `it` used) -- possibly with the first chunks of the next tile, whose
+      // convolution ran on the tensor pipe meanwhile
       if (it + Cfg::NZ < npairs2) drain(it + Cfg::NZ);
     }
   }

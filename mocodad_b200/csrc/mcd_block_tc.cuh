@@ -133,6 +133,22 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// The wait names the loaded registers as in/out operands: every use of them is ordered after it by data dependence.
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -831,57 +847,115 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_tc_kernel(const Blo
       WAIT(0, BAR(BAR_ACC_FULL + set), uint32_t((ti / 2) & 1));
       if (warp == kTcEpiWarp0) TRACE(4, ti, 1);
       tc_fence_after();
+      if constexpr (NW == 1) {
+        // Column groups of 16 channels outermost, 128-row tiles inside: the group's bias (and, for one-window tiles, its
+        // embedding values -- the same for every row) are read from shared memory ONCE per tile instead of once per row tile.
+        // With the row tiles outermost those broadcast loads were 14-20 % of the kernel's shared-memory wavefronts, the pipe
+        // the mixes are bound by (ncu, 64->64 block at 12 joints: 384 of 2 740 wavefronts per chunk).
 #pragma unroll 1
-      for (int m = 0; m < MT; ++m) {
-        const int r = m * 128 + q * 32 + lane;
-        const int wl = r / P;
-        const int64_t w = tile * NW + wl;
-        const bool ok = (r < ROWS) && (w < io.n);
-        const float* embp = sEmb + (ok ? wl : 0) * COUT;
-        const int pp = r - wl * P;  // consecutive lanes -> consecutive positions: planar-4 loads / stores are contiguous
-#pragma unroll 1
-        for (int c0 = 0; c0 < COUT; c0 += 32) {
-          float4 xr[8];
-          const float* ip = io.in + (ok ? act_off(w, c0 >> 2, pp, CIN, P) : 0);
-          float* op = io.out + (ok ? act_off(w, c0 >> 2, pp, COUT, P) : 0);
-          if constexpr (!RESCONV) {  // identity residual: issue the loads of this column group before touching TMEM
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) xr[j4] = ldg_nc4(ip + j4 * P * 4);  // 4-channel planes are P elements apart
-          }
-          uint32_t acc[32];
-          const long long t_ld = MCD_CLOCK();
-          const uint32_t tcol = tmem + (uint32_t(q * 32) << 16) + uint32_t(set * Cfg::ACC_COLS + m * Cfg::TCOLS + c0);
-          tmem_ld32(tcol, acc);
-          uint32_t acc2[Cfg::NMERGE ? 32 : 1];
-          if constexpr (Cfg::NMERGE) tmem_ld32(tcol + COUT, acc2);  // the act_hi * W_lo partial sums
-          // bias / embedding of the first two 4-channel groups travel while the TMEM load is in flight; the rest is
-          // fetched two groups ahead (shared-memory latency is ~100 cycles with the mixes and the tensor pipe on the port)
+        for (int c0 = 0; c0 < COUT; c0 += 16) {
           const float4* bp = reinterpret_cast<const float4*>(sBias + c0);
-          const float4* ep = reinterpret_cast<const float4*>(embp + c0);
-          float4 b4[2] = {bp[0], bp[1]}, e4[2] = {ep[0], ep[1]};
-          tmem_ld_wait(acc);
-          if constexpr (Cfg::NMERGE) {
-            tmem_ld_wait(acc2);
+          const float4* ep = reinterpret_cast<const float4*>(sEmb + c0);
+          const float4 b4[4] = {bp[0], bp[1], bp[2], bp[3]}, e4[4] = {ep[0], ep[1], ep[2], ep[3]};
+#pragma unroll 1
+          for (int m = 0; m < MT; ++m) {
+            const int r = m * 128 + q * 32 + lane;
+            const int wl = r / P;
+            const int64_t w = tile * NW + wl;
+            const bool ok = (r < ROWS) && (w < io.n);
+            const int pp = r - wl * P;  // consecutive lanes -> consecutive positions: planar-4 loads / stores are contiguous
+            float4 xr[4];
+            const float* ip = io.in + (ok ? act_off(w, c0 >> 2, pp, CIN, P) : 0);
+            float* op = io.out + (ok ? act_off(w, c0 >> 2, pp, COUT, P) : 0);
+            if constexpr (!RESCONV) {  // identity residual: issue the loads of this column group before touching TMEM
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(acc2[i]));
-          }
-          PHASE(2, t_ld);
-          const long long t_st = MCD_CLOCK();
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 bc = b4[j4 & 1], ec = e4[j4 & 1];
-            if (j4 + 2 < 8) { b4[j4 & 1] = bp[j4 + 2]; e4[j4 & 1] = ep[j4 + 2]; }
-            float o[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              float v = __uint_as_float(acc[j4 * 4 + jj]) + f4get(bc, jj);
-              if constexpr (!RESCONV) v += f4get(xr[j4], jj);
-              v = v > 0.f ? v : slope * v;
-              o[jj] = v + f4get(ec, jj);
+              for (int j4 = 0; j4 < 4; ++j4) xr[j4] = ldg_nc4(ip + j4 * P * 4);  // 4-channel planes are P elements apart
             }
-            stg4_pred(op + j4 * P * 4, make_float4(o[0], o[1], o[2], o[3]), ok);
+            uint32_t acc[16];
+            const long long t_ld = MCD_CLOCK();
+            const uint32_t tcol = tmem + (uint32_t(q * 32) << 16) + uint32_t(set * Cfg::ACC_COLS + m * Cfg::TCOLS + c0);
+            tmem_ld16(tcol, acc);
+            uint32_t acc2[Cfg::NMERGE ? 16 : 1];
+            if constexpr (Cfg::NMERGE) tmem_ld16(tcol + COUT, acc2);  // the act_hi * W_lo partial sums
+            tmem_ld_wait16(acc);
+            if constexpr (Cfg::NMERGE) {
+              tmem_ld_wait16(acc2);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(acc2[i]));
+            }
+            PHASE(2, t_ld);
+            const long long t_st = MCD_CLOCK();
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              float o[4];
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                float v = __uint_as_float(acc[j4 * 4 + jj]) + f4get(b4[j4], jj);
+                if constexpr (!RESCONV) v += f4get(xr[j4], jj);
+                v = v > 0.f ? v : slope * v;
+                o[jj] = v + f4get(e4[j4], jj);
+              }
+              stg4_pred(op + j4 * P * 4, make_float4(o[0], o[1], o[2], o[3]), ok);
+            }
+            PHASE(3, t_st);
           }
-          PHASE(3, t_st);
+        }
+      } else {
+        // several windows per tile (short windows): the embedding row depends on the row's window, so nothing but the bias
+        // could be hoisted, and 32-channel groups keep twice the identity-residual loads in flight per thread -- with
+        // 16-channel groups the 32->32 blocks at 17 joints ran 36 % slower at T=3 (the epilogue's load latency chain)
+#pragma unroll 1
+        for (int m = 0; m < MT; ++m) {
+          const int r = m * 128 + q * 32 + lane;
+          const int wl = r / P;
+          const int64_t w = tile * NW + wl;
+          const bool ok = (r < ROWS) && (w < io.n);
+          const float* embp = sEmb + (ok ? wl : 0) * COUT;
+          const int pp = r - wl * P;  // consecutive lanes -> consecutive positions: planar-4 loads / stores are contiguous
+#pragma unroll 1
+          for (int c0 = 0; c0 < COUT; c0 += 32) {
+            float4 xr[8];
+            const float* ip = io.in + (ok ? act_off(w, c0 >> 2, pp, CIN, P) : 0);
+            float* op = io.out + (ok ? act_off(w, c0 >> 2, pp, COUT, P) : 0);
+            if constexpr (!RESCONV) {  // identity residual: issue the loads of this column group before touching TMEM
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) xr[j4] = ldg_nc4(ip + j4 * P * 4);  // 4-channel planes are P elements apart
+            }
+            uint32_t acc[32];
+            const long long t_ld = MCD_CLOCK();
+            const uint32_t tcol = tmem + (uint32_t(q * 32) << 16) + uint32_t(set * Cfg::ACC_COLS + m * Cfg::TCOLS + c0);
+            tmem_ld32(tcol, acc);
+            uint32_t acc2[Cfg::NMERGE ? 32 : 1];
+            if constexpr (Cfg::NMERGE) tmem_ld32(tcol + COUT, acc2);  // the act_hi * W_lo partial sums
+            // bias / embedding of the first two 4-channel groups travel while the TMEM load is in flight; the rest is
+            // fetched two groups ahead (shared-memory latency is ~100 cycles with the mixes and the tensor pipe on the port)
+            const float4* bp = reinterpret_cast<const float4*>(sBias + c0);
+            const float4* ep = reinterpret_cast<const float4*>(embp + c0);
+            float4 b4[2] = {bp[0], bp[1]}, e4[2] = {ep[0], ep[1]};
+            tmem_ld_wait(acc);
+            if constexpr (Cfg::NMERGE) {
+              tmem_ld_wait(acc2);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(acc2[i]));
+            }
+            PHASE(2, t_ld);
+            const long long t_st = MCD_CLOCK();
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bc = b4[j4 & 1], ec = e4[j4 & 1];
+              if (j4 + 2 < 8) { b4[j4 & 1] = bp[j4 + 2]; e4[j4 & 1] = ep[j4 + 2]; }
+              float o[4];
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                float v = __uint_as_float(acc[j4 * 4 + jj]) + f4get(bc, jj);
+                if constexpr (!RESCONV) v += f4get(xr[j4], jj);
+                v = v > 0.f ? v : slope * v;
+                o[jj] = v + f4get(ec, jj);
+              }
+              stg4_pred(op + j4 * P * 4, make_float4(o[0], o[1], o[2], o[3]), ok);
+            }
+            PHASE(3, t_st);
+          }
         }
       }
       tc_fence_before();  // accumulator reads ordered before the release of the set
