@@ -260,10 +260,13 @@ constexpr bool kConvFirst = MCD_CONV_FIRST != 0;
 
 // The dense middle blocks: 1x1 channel contraction on the tensor cores.  Blocks that keep or widen the channel count mix
 // first (mcd_block_tc.cuh); blocks that narrow it (Cin > Cout) convolve first and mix on the Cout side (mcd_block_cf.cuh).
-template <int T, int V, int CIN, int COUT>
-int dense_block_op(int action, const mcd_model* m, int slot, const BlockWeights* w, const BlockIO* io, cudaStream_t s) {
+// VUP > 0 (conv-first blocks only): the block also applies the up-path CNN_layer `rs` (V -> VUP joints) and adds io->skip.
+template <int T, int V, int CIN, int COUT, int VUP = 0>
+int dense_block_op(int action, const mcd_model* m, int slot, const BlockWeights* w, const BlockIO* io, cudaStream_t s,
+                   const PackedResample* rs = nullptr) {
   constexpr bool CONV_FIRST = kConvFirst && CIN > COUT;
-  using Tc = std::conditional_t<CONV_FIRST, CfCfg<T, V, CONV_FIRST ? CIN : 2 * COUT, COUT, nw_for(T, 17)>, TcCfg<T, V, CIN, COUT, nw_for(T, 17)>>;
+  static_assert(VUP == 0 || CONV_FIRST, "the fused up-path resample lives in the conv-first kernel");
+  using Tc = std::conditional_t<CONV_FIRST, CfCfg<T, V, CONV_FIRST ? CIN : 2 * COUT, COUT, nw_for(T, 17), VUP>, TcCfg<T, V, CIN, COUT, nw_for(T, 17)>>;
   static_assert(Tc::SMEM_BYTES <= 227 * 1024, "tensor-core block kernel exceeds the 227 KB shared memory of an sm_100 CTA");
   auto kernel = [] {
     if constexpr (CONV_FIRST) return stgcn_block_cf_kernel<Tc>;
@@ -284,7 +287,20 @@ int dense_block_op(int action, const mcd_model* m, int slot, const BlockWeights*
   if (Tc::TMA_TILED) MCD_TRY(make_x_tensor_map(&tmx, io->in, io->n, CIN, T, V, Tc::NW));
   {
     LaunchScope ls(m, slot, io->n, s);
-    kernel<<<grid, kTcThreads, Tc::SMEM_BYTES, s>>>(*w, io2, tmx);
+    if constexpr (CONV_FIRST) {
+      typename Tc::Up up{};
+      if constexpr (VUP > 0) {
+        if (rs == nullptr || rs->vin != V || rs->vout != VUP || io->skip == nullptr)
+          return fail(MCD_ERR_INVALID_ARG, "block %s: fused resample needs the %d->%d CNN_layer and a skip tensor", kSlotNames[slot], V, VUP);
+        for (int wv = 0; wv < VUP; ++wv) {
+          for (int v = 0; v < V; ++v) up.w[wv][v] = rs->hW[size_t(wv) * V + v];
+          up.b[wv] = rs->hb[wv];
+        }
+      }
+      kernel<<<grid, kTcThreads, Tc::SMEM_BYTES, s>>>(*w, io2, tmx, up);
+    } else {
+      kernel<<<grid, kTcThreads, Tc::SMEM_BYTES, s>>>(*w, io2, tmx);
+    }
   }
   return check_launch(kSlotNames[slot]);
 }
@@ -312,6 +328,17 @@ int edge_block_op(int action, const mcd_model* m, int slot, const BlockWeights* 
   return check_launch(kSlotNames[slot]);
 }
 
+#ifndef MCD_FUSE_UP
+#define MCD_FUSE_UP 1
+#endif
+// Up path, production calls at T=24: block 6 (st_gcnnsd3.1, conv-first) also applies the CNN_layer that follows it (`up3`,
+// 10 -> 12 joints) and the skip add, and writes the 12-joint tensor -- no stand-alone resample launch, no round trip of the
+// block's own output through HBM (measured: 41.8 ms instead of 28.3 + 18.7 ms per step).  Not used where it measured slower:
+// block 8 + `up2` (the 12 -> 17 resample is 47 % of that block's mix FMAs and lands on the same issue-bound sub-partitions:
+// 41.7 ms instead of 16.6 + 12.9 ms) and short windows (T=3: 6.7 instead of 3.7 + 2.4 ms).  Layer taps and the latent
+// variant's down half use the unfused kernels; both paths agree bit for bit (tests/test_gpu_parity.py).
+constexpr bool fuse_up_block(int T, int idx) { return kConvFirst && MCD_FUSE_UP != 0 && T == 24 && idx == 6; }
+
 template <int T>
 int unet_block_op(int action, int idx, const mcd_model* m, const BlockWeights* w, const BlockIO* io, cudaStream_t s) {
   const int slot = SLOT_UNET0 + idx;
@@ -329,6 +356,15 @@ int unet_block_op(int action, int idx, const mcd_model* m, const BlockWeights* w
     case 10: return edge_block_op<T, false>(action, m, slot, w, io, s);
   }
   return fail(MCD_ERR_INVALID_ARG, "bad U-Net block index %d", idx);
+}
+
+template <int T>
+int unet_block_up_op(int action, int idx, const mcd_model* m, const BlockWeights* w, const BlockIO* io, cudaStream_t s) {
+  const int slot = SLOT_UNET0 + idx;
+  if constexpr (fuse_up_block(T, 6)) {
+    if (idx == 6) return dense_block_op<T, 10, 128, 64, 12>(action, m, slot, w, io, s, &m->rs[2]);  // + up3 (10 -> 12 joints) + d2
+  }
+  return fail(MCD_ERR_INVALID_ARG, "U-Net block %d has no fused up-path variant at T=%d", idx, T);
 }
 
 template <int TC>
@@ -353,6 +389,15 @@ int unet_block_dispatch(int action, int T, int idx, const mcd_model* m, const Bl
                         cudaStream_t s) {
   switch (T) {
 #define X(t_) case t_: return unet_block_op<t_>(action, idx, m, w, io, s);
+    MCD_FOR_EACH_T(X)
+#undef X
+  }
+  return fail(MCD_ERR_UNSUPPORTED, "no denoiser kernels compiled for T=%d frames", T);
+}
+int unet_block_up_dispatch(int action, int T, int idx, const mcd_model* m, const BlockWeights* w, const BlockIO* io,
+                           cudaStream_t s) {
+  switch (T) {
+#define X(t_) case t_: return unet_block_up_op<t_>(action, idx, m, w, io, s);
     MCD_FOR_EACH_T(X)
 #undef X
   }
@@ -479,9 +524,12 @@ int unet_forward_impl(const mcd_model* m, const float* d_x, int64_t n, int t, co
     }
     return check_launch("tap");
   };
-  auto block = [&](int idx, const float* in, float* out) -> int {
+  // production calls (no layer tap, whole denoiser) run the up path with the CNN_layers fused into blocks 6 and 8
+  const bool fuse6 = fuse_up_block(T, 6) && tap == nullptr && down_out == nullptr;
+  auto block = [&](int idx, const float* in, float* out, const float* fused_skip = nullptr) -> int {
     io.in = in;
     io.out = out;
+    io.skip = fused_skip;
     io.in_sn = 0; io.in_sc = 0; io.in_t0 = 0; io.xres = nullptr;
     io.emb_off = m->emb_off[idx];
     if (idx == 0) {
@@ -497,6 +545,7 @@ int unet_forward_impl(const mcd_model* m, const float* d_x, int64_t n, int t, co
         io.out = const_cast<float*>(d_x);
       }
     }
+    if (fused_skip != nullptr) return unet_block_up_dispatch(1, T, idx, m, &m->unet[idx].w, &io, s);
     MCD_TRY(unet_block_dispatch(1, T, idx, m, &m->unet[idx].w, &io, s));
     if (idx != kNumUnetBlocks - 1) MCD_TRY(tap_copy(kUnetBlocks[idx].name, out, kUnetBlocks[idx].cout, kPyramid[kUnetBlocks[idx].level]));
     return MCD_OK;
@@ -534,6 +583,15 @@ int unet_forward_impl(const mcd_model* m, const float* d_x, int64_t n, int t, co
   MCD_TRY(block(4, ws.bufB, ws.d2));
   MCD_TRY(resample(1, ws.d2, nullptr, ws.bufA, 64));
   MCD_TRY(block(5, ws.bufA, ws.bufB));
+  if (fuse6) {
+    MCD_TRY(block(6, ws.bufB, ws.bufA, ws.d2));   // st_gcnnsd3.1 + up3 + d2  -> [n, 64, T, 12]
+    MCD_TRY(block(7, ws.bufA, ws.bufB));
+    MCD_TRY(block(8, ws.bufB, ws.bufA));
+    MCD_TRY(resample(3, ws.bufA, ws.d1, ws.bufB, 32));
+    MCD_TRY(block(9, ws.bufB, ws.bufA));
+    MCD_TRY(block(10, ws.bufA, d_eps));
+    return MCD_OK;
+  }
   MCD_TRY(block(6, ws.bufB, ws.bufA));
   if (down_out != nullptr) { *down_out = ws.bufA; return MCD_OK; }
   MCD_TRY(resample(2, ws.bufA, ws.d2, ws.bufB, 64));
@@ -1147,6 +1205,7 @@ int mcd_model_finalize(mcd_model* m) {
   m->d_pos = m->d_arena + pos_off;
   for (int i = 0; i < m->n_blocks; ++i) MCD_TRY(unet_block_dispatch(0, m->T, i, m, nullptr, nullptr, nullptr));
   for (int i = 0; i < m->n_rs; ++i) MCD_TRY(resample_dispatch(0, m, i, nullptr, nullptr, nullptr, 0, 0, nullptr));
+  if (fuse_up_block(m->T, 6) && !m->latent) MCD_TRY(unet_block_up_dispatch(0, m->T, 6, m, nullptr, nullptr, nullptr));
   if (m->Tc > 0)
     for (int i = 0; i < kNumEncBlocks; ++i) MCD_TRY(enc_block_dispatch(0, m->Tc, i, m, nullptr, nullptr, nullptr));
   m->finalized = true;
@@ -1627,6 +1686,11 @@ int mcd_profile_slot_cost(const mcd_model* m, int slot, double* bytes_per_window
   if (slot < SLOT_RS0) {
     const BlockShape& b = kUnetBlocks[slot];
     block_cost(b.cin, b.cout, m->T, kPyramid[b.level], true, slot == 0, slot == kNumUnetBlocks - 1);
+    if (fuse_up_block(m->T, slot)) {  // production path: + the fused CNN_layer and skip add (the block's own output stays on chip)
+      const int vin = kPyramid[b.level], vout = kPyramid[b.level - 1];
+      bytes = 4.0 * m->T * (double(b.cin) * vin + 2.0 * b.cout * vout);
+      flops += 2.0 * b.cout * m->T * vin * vout;
+    }
   } else if (slot < SLOT_DDPM) {
     const ResampleShape& r = kResample[slot - SLOT_RS0];
     const int vin = kPyramid[r.lin], vout = kPyramid[r.lout];

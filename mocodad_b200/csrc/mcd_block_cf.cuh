@@ -24,14 +24,26 @@
 //   warps 4-7  A-mix  Y2[t,w,c] = sum_v Y1[t,v,c] * A[t][v][w]      -> planar fp32 chunk for the final stage
 // The convolution of tile i+1 (tensor pipe) overlaps the mixes of tile i (FMA pipe); TMEM holds two accumulator sets.
 #pragma once
+#include <type_traits>
 #include "mcd_block_tc.cuh"
 
 namespace mcd {
 
-template <int T_, int V_, int CIN_, int COUT_, int NW_>
+struct CfNoUp { int unused; };
+
+// VUP_ > 0: the block also applies the CNN_layer that follows it on the up path (joint resample V -> VUP with folded
+// BatchNorm, stsgcn.py:187-199 at stsae_unet.py:381-394) and the U-Net skip add, and writes the VUP-joint tensor
+template <int T_, int V_, int CIN_, int COUT_, int NW_, int VUP_ = 0>
 struct CfCfg {
   using Mix = TcCfg<T_, V_, COUT_, COUT_, NW_>;  // task shapes of the two mixes (they depend on T, V and the window count only)
-  static constexpr int T = T_, V = V_, CIN = CIN_, COUT = COUT_, NW = NW_;
+  static constexpr int T = T_, V = V_, CIN = CIN_, COUT = COUT_, NW = NW_, VUP = VUP_;
+  using Up = std::conditional_t<(VUP_ > 0), ResampleParams<V_, (VUP_ > 0 ? VUP_ : 1)>, CfNoUp>;
+  // fused resample: an epilogue thread owns UP_WG output joints (g, g + UP_NG, ...) of the frames fg, fg + UP_FG, ... of the tile
+  static constexpr int UP_WG = 3;
+  static constexpr int UP_NG = (VUP_ + UP_WG - 1) / UP_WG;
+  static constexpr int FRAMES = NW_ * T_;
+  static constexpr int UP_FG = VUP_ > 0 ? ((kTcEpilogue / (UP_NG > 0 ? UP_NG : 1)) < FRAMES ? (kTcEpilogue / (UP_NG > 0 ? UP_NG : 1)) : FRAMES) : 1;
+  static constexpr int UP_ROUNDS = (FRAMES + UP_FG - 1) / UP_FG;
   static constexpr int P = T * V, ROWS = NW * P, MT = (ROWS + 127) / 128;
   static constexpr int KC = 16, C4 = 4;
   static constexpr int NCHUNK = CIN / KC;   // input chunks (convolution K steps)
@@ -46,7 +58,8 @@ struct CfCfg {
   static constexpr int ARR = ROWS * 16;            // one 16-channel planar chunk [c4][row][4 floats]
   static constexpr int Y1ARR = Mix::Y1ARR;
   static constexpr int WCH = 4 * COUT * 16;        // one chunk of weight operands: [W hi | Wr hi | W lo | Wr lo] x [COUT][16]
-  static constexpr int SM_MISC = 2 * Y1ARR + 2 * WCH + COUT + NW * COUT;
+  static constexpr int UPW_FLOATS = VUP_ > 0 ? (VUP_ * (V_ + 1) + 3) / 4 * 4 : 0;  // fused resample: W[w][0..V) and b[w] per output joint
+  static constexpr int SM_MISC = 2 * Y1ARR + 2 * WCH + COUT + NW * COUT + UPW_FLOATS;
   static constexpr bool fits(int arrays) { return size_t(SM_MISC + arrays * ARR) * sizeof(float) + 1024 <= 227 * 1024; }
   // arrays: X ring (NXB), Xlo (2: one per conversion warp), Z ring (NZ = 2), Y2 (2).  The X ring takes what is left, up to 4
   // slots: a slot's round trip is release (MMA commit) -> TMA issue -> landed -> conversion -> MMAs, ~4 k cycles, so a ring of 2
@@ -63,7 +76,8 @@ struct CfCfg {
   static constexpr int SM_WC = SM_Y1 + 2 * Y1ARR;
   static constexpr int SM_BIAS = SM_WC + 2 * WCH;
   static constexpr int SM_EMB = SM_BIAS + COUT;
-  static constexpr int SM_TOTAL = SM_EMB + NW * COUT;
+  static constexpr int SM_UP = SM_EMB + NW * COUT;
+  static constexpr int SM_TOTAL = SM_UP + UPW_FLOATS;
   // the last 128-row MMA tile over-reads (MT*128 - ROWS) rows past each plane of X / Xlo: the arrays that follow absorb it
   static_assert((MT * 128 - ROWS) * 4 <= NZ * ARR, "over-read of the last MMA tile must stay inside the allocation");
   static constexpr size_t SMEM_BYTES = size_t(SM_TOTAL) * sizeof(float) + 1024;
@@ -88,12 +102,14 @@ enum CfBar {
 
 template <class Cfg>
 __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_cf_kernel(const BlockWeights wt, const BlockIO io,
-                                                                       const __grid_constant__ CUtensorMap tmx) {
+                                                                       const __grid_constant__ CUtensorMap tmx,
+                                                                       const __grid_constant__ typename Cfg::Up up) {
   using Mix = typename Cfg::Mix;
   constexpr int T = Cfg::T, V = Cfg::V, P = Cfg::P, ROWS = Cfg::ROWS, C4 = Cfg::C4, MT = Cfg::MT;
   constexpr int CIN = Cfg::CIN, COUT = Cfg::COUT, NCHUNK = Cfg::NCHUNK, NCH2 = Cfg::NCH2, NW = Cfg::NW, NXB = Cfg::NXB;
   constexpr int VP = Mix::VP, TP4 = Mix::TP4, TMS = Mix::TMS, ARR = Cfg::ARR, WCH = Cfg::WCH;
   constexpr int QG = Mix::QG, NQG = Mix::NQG, WGS = Mix::WGS, NWG = Mix::NWG, TTP = Mix::TTP, Y1ARR = Cfg::Y1ARR;
+  constexpr int VUP = Cfg::VUP;
 
   extern __shared__ uint8_t smem_raw[];
   float* smem = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -144,8 +160,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_cf_kernel(const Blo
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp >= kTcEpiWarp0 && warp < kTcLoadWarp)
+  if (warp >= kTcEpiWarp0 && warp < kTcLoadWarp) {
     for (int i = tid - kTcEpiWarp0 * 32; i < COUT; i += kTcEpilogue) sBias[i] = wt.bias[i];
+    if constexpr (VUP > 0) {
+      // the fused CNN_layer's weights: the threads of a warp own different output joints, and per-lane indices into the
+      // parameter (constant) bank serialise -- shared memory serves them in one wavefront
+      float* sUp = smem + Cfg::SM_UP;
+      for (int i = tid - kTcEpiWarp0 * 32; i < VUP * (V + 1); i += kTcEpilogue) {
+        const int w = i / (V + 1), v = i - w * (V + 1);
+        sUp[i] = v < V ? up.w[w][v] : up.b[w];
+      }
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -439,7 +465,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_cf_kernel(const Blo
       const int ti = it / NCH2, c = it - ti * NCH2, s = it & 1, set = ti & 1;
       const int64_t tile = blockIdx.x + int64_t(ti) * gridDim.x;
       mbar_wait(BAR(CF_Y2_FULL + s), uint32_t((it / 2) & 1));
-      const float* y2 = sY2 + s * ARR;
+      float* y2 = sY2 + s * ARR;
       // the chunk's bias (and, for one-window tiles, its embedding values) are the same for every row: read once per chunk
       constexpr bool EMB_HOIST = NW == 1;
       const float4* bp = reinterpret_cast<const float4*>(sBias + c * 16);
@@ -478,13 +504,93 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_cf_kernel(const Blo
             x = x > 0.f ? x : slope * x;
             o[jj] = x + f4get(e4[j], jj);
           }
-          stg4_pred(op + j * P * 4, make_float4(o[0], o[1], o[2], o[3]), ok);
+          if constexpr (VUP == 0) stg4_pred(op + j * P * 4, make_float4(o[0], o[1], o[2], o[3]), ok);
+          else sts4_pred(y2 + (j * ROWS + (r < ROWS ? r : 0)) * 4, make_float4(o[0], o[1], o[2], o[3]), r < ROWS);  // in place: the thread's own row
         }
       }
-      mbar_arrive(BAR(CF_Y2_EMPTY + s));
+      if constexpr (VUP == 0) mbar_arrive(BAR(CF_Y2_EMPTY + s));  // (fused resample: released by upsample())
       if (c == NCH2 - 1) {
         tc_fence_before();  // accumulator reads ordered before the release of the set
         mbar_arrive(BAR(CF_ACC_EMPTY + set));
+      }
+    };
+
+    // Fused CNN_layer + skip add (VUP > 0): the chunk's block outputs sit in Y2 slot s (written in place by final_stage);
+    //   out[n, c, t, w] = b[w] + sum_v W[w][v] * y[n, c, t, v] + skip[n, c, t, w]        (same operation order as
+    // joint_resample_kernel, so the fused and the stand-alone path agree bit for bit).  A thread owns the output joints
+    // g, g + UP_NG, ... of frames fg, fg + UP_FG, ...: consecutive threads store consecutive 16-byte elements.
+    // Work items of a chunk: k = round * C4 + c4 (frame f = fg + round * UP_FG, 4-channel plane c4).  The skip loads run two
+    // items ahead of the arithmetic (global latency ~800 cycles against ~300 cycles of work per item), the first two are
+    // issued before the drain of the next Z chunk.
+    constexpr int UPW = VUP > 0 ? Cfg::UP_WG : 1;
+    struct UpSkip { float4 a[UPW], b[UPW]; };
+    const int up_fg = etid / (VUP > 0 ? Cfg::UP_NG : 1), up_g = etid - up_fg * (VUP > 0 ? Cfg::UP_NG : 1);
+    auto up_item = [&](int it, int k, int64_t& o0) -> bool {  // global offset of (frame, plane, joint g); false: nothing to do
+      const int ti = it / NCH2, c = it - ti * NCH2;
+      const int64_t tile = blockIdx.x + int64_t(ti) * gridDim.x;
+      const int f = up_fg + (k / C4) * Cfg::UP_FG, c4 = k % C4;
+      const int wl = f / T, t = f - wl * T;
+      const int64_t wdw = tile * NW + wl;
+      o0 = act_off(wdw, c * 4 + c4, t * VUP + up_g, COUT, T * VUP);
+      return up_fg < Cfg::UP_FG && f < Cfg::FRAMES && wdw < io.n;
+    };
+    auto up_load = [&](int it, int k, float4* sk) {
+      int64_t o0;
+      if (up_item(it, k, o0)) {
+#pragma unroll
+        for (int j = 0; j < UPW; ++j)
+          if (up_g + j * Cfg::UP_NG < VUP) sk[j] = ldg_nc4(io.skip + o0 + int64_t(j) * Cfg::UP_NG * 4);
+      }
+    };
+    auto up_begin = [&](int it, UpSkip& st) {
+      if constexpr (VUP > 0) { up_load(it, 0, st.a); up_load(it, 1, st.b); }
+    };
+    auto up_finish = [&](int it, UpSkip& st) {
+      if constexpr (VUP > 0) {
+        constexpr int WG = Cfg::UP_WG, NG = Cfg::UP_NG, K = Cfg::UP_ROUNDS * C4;
+        static_assert(K % 2 == 0, "items are processed in pairs");
+        const int s = it & 1;
+        named_bar_sync(3, kTcEpilogue);  // every row of the chunk is in place
+        float rw[WG][V], rb[WG];
+#pragma unroll
+        for (int j = 0; j < WG; ++j) {
+          const float* wp = smem + Cfg::SM_UP + (up_g + j * NG < VUP ? up_g + j * NG : 0) * (V + 1);
+          rb[j] = wp[V];
+#pragma unroll
+          for (int v = 0; v < V; ++v) rw[j][v] = wp[v];
+        }
+        const float* y2 = sY2 + s * ARR;
+        auto compute = [&](int k, const float4* sk) {
+          int64_t o0;
+          if (!up_item(it, k, o0)) return;
+          const int f = up_fg + (k / C4) * Cfg::UP_FG, c4 = k % C4;
+          float4 a[WG];
+#pragma unroll
+          for (int j = 0; j < WG; ++j) a[j] = make_float4(rb[j], rb[j], rb[j], rb[j]);
+          const float* xp = y2 + (c4 * ROWS + f * V) * 4;
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const float4 x = *reinterpret_cast<const float4*>(xp + v * 4);
+#pragma unroll
+            for (int j = 0; j < WG; ++j) {
+              a[j].x = fmaf(rw[j][v], x.x, a[j].x); a[j].y = fmaf(rw[j][v], x.y, a[j].y);
+              a[j].z = fmaf(rw[j][v], x.z, a[j].z); a[j].w = fmaf(rw[j][v], x.w, a[j].w);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < WG; ++j)
+            if (up_g + j * NG < VUP)
+              stg4_pred(io.out + o0 + int64_t(j) * NG * 4,
+                        make_float4(a[j].x + sk[j].x, a[j].y + sk[j].y, a[j].z + sk[j].z, a[j].w + sk[j].w), true);
+        };
+#pragma unroll 1
+        for (int k = 0; k < K; k += 2) {
+          compute(k, st.a);
+          if (k + 2 < K) up_load(it, k + 2, st.a);
+          compute(k + 1, st.b);
+          if (k + 3 < K) up_load(it, k + 3, st.b);
+        }
+        mbar_arrive(BAR(CF_Y2_EMPTY + s));
       }
     };
 
@@ -504,7 +610,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_cf_kernel(const Blo
       // refill the Z slot this chunk's mixes released (the A-mix of `it` is done, hence its T-mix; NZ = 2 = the Y2 ring depth, so
       // slot (it + NZ) % NZ is the one iteration `it` used) -- possibly with the first chunks of the next tile, whose
       // convolution ran on the tensor pipe meanwhile
+      UpSkip st;
+      up_begin(it, st);
       if (it + Cfg::NZ < npairs2) drain(it + Cfg::NZ);
+      up_finish(it, st);  // (after the drain: the T-mix warps get their next chunk first)
     }
   }
 
