@@ -543,7 +543,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_cf_kernel(const Blo
       }
     };
     auto up_begin = [&](int it, UpSkip& st) {
-      if constexpr (VUP > 0) { up_load(it, 0, st.a); up_load(it, 1, st.b); }
+      if constexpr (VUP > 0) {
+        up_load(it, 0, st.a);
+        up_load(it, 1, st.b);
+        // The skip tensor was written several kernels ago and comes from HBM; its loads are two thirds of this stage's cost
+        // (by elimination: 41.8 -> 32.3 ms per step without them).  Pull the NEXT chunk's rows into L2 now, a whole chunk period
+        // ahead: the register loads then see L2 latency, which the two-item look-ahead covers better (43.3 -> 42.0 ms).
+        // (Requesting all of a chunk's skip values into registers before the drain measured slower: 50.9 ms.)
+        if (it + 1 < npairs2) {
+#pragma unroll
+          for (int k = 0; k < Cfg::UP_ROUNDS * C4; ++k) {
+            int64_t o0;
+            if (up_item(it + 1, k, o0)) {
+#pragma unroll
+              for (int j = 0; j < UPW; ++j)
+                if (up_g + j * Cfg::UP_NG < VUP)
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(io.skip + o0 + int64_t(j) * Cfg::UP_NG * 4));
+            }
+          }
+        }
+      }
     };
     auto up_finish = [&](int it, UpSkip& st) {
       if constexpr (VUP > 0) {
