@@ -484,10 +484,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_cf_kernel(const Blo
         const int pp = r - wl * P;
         uint32_t acc[16];
         tmem_ld16(tmem + (uint32_t(q * 32) << 16) + uint32_t(set * Cfg::ACC_COLS + m * Cfg::TCOLS + COUT + c * 16), acc);
-        const int rr = ok ? r : 0;
+        // rows past the tile (r >= ROWS) read a dummy location nobody writes: with the fused resample the chunk is rewritten
+        // in place by the rows' owners while other threads may still be loading
         float4 y[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) y[j] = *reinterpret_cast<const float4*>(y2 + (j * ROWS + rr) * 4);
+        for (int j = 0; j < 4; ++j) y[j] = *reinterpret_cast<const float4*>(r < ROWS ? y2 + (j * ROWS + r) * 4 : sBias + j * 4);
         if constexpr (!EMB_HOIST) {
           const float4* ep = reinterpret_cast<const float4*>(sEmb + (ok ? wl : 0) * COUT + c * 16);
 #pragma unroll

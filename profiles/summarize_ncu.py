@@ -16,8 +16,8 @@ import sys
 SLOT_OF = [  # kernel-name pattern -> profile slot name (mcd_profile_slot_name); first match wins
     (r"TcCfg<(?:\(int\))?\d+, (?:\(int\))?17, (?:\(int\))?16, (?:\(int\))?32", "st_gcnnsd1.0"), (r"TcCfg<(?:\(int\))?\d+, (?:\(int\))?17, (?:\(int\))?32, (?:\(int\))?32", "st_gcnnsd1.1|st_gcnnsu3.0"),
     (r"TcCfg<(?:\(int\))?\d+, (?:\(int\))?12, (?:\(int\))?32, (?:\(int\))?64", "st_gcnnsd2.0"), (r"TcCfg<(?:\(int\))?\d+, (?:\(int\))?12, (?:\(int\))?64, (?:\(int\))?64", "st_gcnnsd2.1|st_gcnnsu4.0"),
-    (r"TcCfg<(?:\(int\))?\d+, (?:\(int\))?10, (?:\(int\))?64, (?:\(int\))?128", "st_gcnnsd3.0"), (r"TcCfg<(?:\(int\))?\d+, (?:\(int\))?10, (?:\(int\))?128, (?:\(int\))?64", "st_gcnnsd3.1"),
-    (r"TcCfg<(?:\(int\))?\d+, (?:\(int\))?12, (?:\(int\))?64, (?:\(int\))?32", "st_gcnnsu4.1"),
+    (r"TcCfg<(?:\(int\))?\d+, (?:\(int\))?10, (?:\(int\))?64, (?:\(int\))?128", "st_gcnnsd3.0"), (r"(?:Tc|Cf)Cfg<(?:\(int\))?\d+, (?:\(int\))?10, (?:\(int\))?128, (?:\(int\))?64", "st_gcnnsd3.1"),
+    (r"(?:Tc|Cf)Cfg<(?:\(int\))?\d+, (?:\(int\))?12, (?:\(int\))?64, (?:\(int\))?32", "st_gcnnsu4.1"),
     (r"EdgeCfg<(?:\(int\))?\d+, (?:\(int\))?17, (?:\(int\))?\d+, (?:\(bool\))?1", "st_gcnnsp1a.0"), (r"EdgeCfg<(?:\(int\))?\d+, (?:\(int\))?17, (?:\(int\))?\d+, (?:\(bool\))?0", "st_gcnnsu3.1"),
     (r"joint_resample_kernel<(?:\(int\))?17, (?:\(int\))?12", "down1"), (r"joint_resample_kernel<(?:\(int\))?12, (?:\(int\))?10", "down2"),
     (r"joint_resample_kernel<(?:\(int\))?10, (?:\(int\))?12", "up3"), (r"joint_resample_kernel<(?:\(int\))?12, (?:\(int\))?17", "up2"),
