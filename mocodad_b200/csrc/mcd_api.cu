@@ -290,8 +290,9 @@ int dense_block_op(int action, const mcd_model* m, int slot, const BlockWeights*
     if constexpr (CONV_FIRST) {
       typename Tc::Up up{};
       if constexpr (VUP > 0) {
-        if (rs == nullptr || rs->vin != V || rs->vout != VUP || io->skip == nullptr)
-          return fail(MCD_ERR_INVALID_ARG, "block %s: fused resample needs the %d->%d CNN_layer and a skip tensor", kSlotNames[slot], V, VUP);
+        if (rs == nullptr || rs->vin != V || rs->vout != VUP || io->skip == nullptr || io->skip != io->out)
+          return fail(MCD_ERR_INVALID_ARG, "block %s: fused resample needs the %d->%d CNN_layer and accumulates onto the skip tensor in place",
+                      kSlotNames[slot], V, VUP);
         for (int wv = 0; wv < VUP; ++wv) {
           for (int v = 0; v < V; ++v) up.w[wv][v] = rs->hW[size_t(wv) * V + v];
           up.b[wv] = rs->hb[wv];
@@ -337,7 +338,7 @@ int edge_block_op(int action, const mcd_model* m, int slot, const BlockWeights* 
 // block 8 + `up2` (the 12 -> 17 resample is 47 % of that block's mix FMAs and lands on the same issue-bound sub-partitions:
 // 41.7 ms instead of 16.6 + 12.9 ms) and short windows (T=3: 6.7 instead of 3.7 + 2.4 ms).  Layer taps and the latent
 // variant's down half use the unfused kernels; both paths agree bit for bit (tests/test_gpu_parity.py).
-constexpr bool fuse_up_block(int T, int idx) { return kConvFirst && MCD_FUSE_UP != 0 && T == 24 && idx == 6; }
+constexpr bool fuse_up_block(int T, int idx) { return kConvFirst && MCD_FUSE_UP != 0 && (idx == 6 || idx == 8) && T > 0; }
 
 template <int T>
 int unet_block_op(int action, int idx, const mcd_model* m, const BlockWeights* w, const BlockIO* io, cudaStream_t s) {
@@ -362,7 +363,10 @@ template <int T>
 int unet_block_up_op(int action, int idx, const mcd_model* m, const BlockWeights* w, const BlockIO* io, cudaStream_t s) {
   const int slot = SLOT_UNET0 + idx;
   if constexpr (fuse_up_block(T, 6)) {
-    if (idx == 6) return dense_block_op<T, 10, 128, 64, 12>(action, m, slot, w, io, s, &m->rs[2]);  // + up3 (10 -> 12 joints) + d2
+    if (idx == 6) return dense_block_op<T, 10, 128, 64, 12>(action, m, slot, w, io, s, &m->rs[2]);  // + up3 (10 -> 12 joints) onto d2
+  }
+  if constexpr (fuse_up_block(T, 8)) {
+    if (idx == 8) return dense_block_op<T, 12, 64, 32, 17>(action, m, slot, w, io, s, &m->rs[3]);   // + up2 (12 -> 17 joints) onto d1
   }
   return fail(MCD_ERR_INVALID_ARG, "U-Net block %d has no fused up-path variant at T=%d", idx, T);
 }
@@ -526,6 +530,7 @@ int unet_forward_impl(const mcd_model* m, const float* d_x, int64_t n, int t, co
   };
   // production calls (no layer tap, whole denoiser) run the up path with the CNN_layers fused into blocks 6 and 8
   const bool fuse6 = fuse_up_block(T, 6) && tap == nullptr && down_out == nullptr;
+  const bool fuse8 = fuse_up_block(T, 8) && tap == nullptr && down_out == nullptr;
   auto block = [&](int idx, const float* in, float* out, const float* fused_skip = nullptr) -> int {
     io.in = in;
     io.out = out;
@@ -583,23 +588,28 @@ int unet_forward_impl(const mcd_model* m, const float* d_x, int64_t n, int t, co
   MCD_TRY(block(4, ws.bufB, ws.d2));
   MCD_TRY(resample(1, ws.d2, nullptr, ws.bufA, 64));
   MCD_TRY(block(5, ws.bufA, ws.bufB));
+  const float* cur;
   if (fuse6) {
-    MCD_TRY(block(6, ws.bufB, ws.bufA, ws.d2));   // st_gcnnsd3.1 + up3 + d2  -> [n, 64, T, 12]
-    MCD_TRY(block(7, ws.bufA, ws.bufB));
-    MCD_TRY(block(8, ws.bufB, ws.bufA));
-    MCD_TRY(resample(3, ws.bufA, ws.d1, ws.bufB, 32));
-    MCD_TRY(block(9, ws.bufB, ws.bufA));
-    MCD_TRY(block(10, ws.bufA, d_eps));
-    return MCD_OK;
+    MCD_TRY(block(6, ws.bufB, ws.d2, ws.d2));     // st_gcnnsd3.1 + up3, accumulated onto d2  -> [n, 64, T, 12]
+    cur = ws.d2;
+  } else {
+    MCD_TRY(block(6, ws.bufB, ws.bufA));
+    if (down_out != nullptr) { *down_out = ws.bufA; return MCD_OK; }
+    MCD_TRY(resample(2, ws.bufA, ws.d2, ws.bufB, 64));
+    cur = ws.bufB;
   }
-  MCD_TRY(block(6, ws.bufB, ws.bufA));
-  if (down_out != nullptr) { *down_out = ws.bufA; return MCD_OK; }
-  MCD_TRY(resample(2, ws.bufA, ws.d2, ws.bufB, 64));
-  MCD_TRY(block(7, ws.bufB, ws.bufA));
-  MCD_TRY(block(8, ws.bufA, ws.bufB));
-  MCD_TRY(resample(3, ws.bufB, ws.d1, ws.bufA, 32));
-  MCD_TRY(block(9, ws.bufA, ws.bufB));
-  MCD_TRY(block(10, ws.bufB, d_eps));
+  MCD_TRY(block(7, cur, ws.bufA));
+  if (fuse8) {
+    MCD_TRY(block(8, ws.bufA, ws.d1, ws.d1));     // st_gcnnsu4.1 + up2, accumulated onto d1  -> [n, 32, T, 17]
+    cur = ws.d1;
+  } else {
+    MCD_TRY(block(8, ws.bufA, ws.bufB));
+    MCD_TRY(resample(3, ws.bufB, ws.d1, ws.bufA, 32));
+    cur = ws.bufA;
+  }
+  float* out9 = cur == ws.bufA ? ws.bufB : ws.bufA;
+  MCD_TRY(block(9, cur, out9));
+  MCD_TRY(block(10, out9, d_eps));
   return MCD_OK;
 }
 
@@ -1206,6 +1216,7 @@ int mcd_model_finalize(mcd_model* m) {
   for (int i = 0; i < m->n_blocks; ++i) MCD_TRY(unet_block_dispatch(0, m->T, i, m, nullptr, nullptr, nullptr));
   for (int i = 0; i < m->n_rs; ++i) MCD_TRY(resample_dispatch(0, m, i, nullptr, nullptr, nullptr, 0, 0, nullptr));
   if (fuse_up_block(m->T, 6) && !m->latent) MCD_TRY(unet_block_up_dispatch(0, m->T, 6, m, nullptr, nullptr, nullptr));
+  if (fuse_up_block(m->T, 8) && !m->latent) MCD_TRY(unet_block_up_dispatch(0, m->T, 8, m, nullptr, nullptr, nullptr));
   if (m->Tc > 0)
     for (int i = 0; i < kNumEncBlocks; ++i) MCD_TRY(enc_block_dispatch(0, m->Tc, i, m, nullptr, nullptr, nullptr));
   m->finalized = true;

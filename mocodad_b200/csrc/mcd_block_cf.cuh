@@ -32,14 +32,15 @@ namespace mcd {
 struct CfNoUp { int unused; };
 
 // VUP_ > 0: the block also applies the CNN_layer that follows it on the up path (joint resample V -> VUP with folded
-// BatchNorm, stsgcn.py:187-199 at stsae_unet.py:381-394) and the U-Net skip add, and writes the VUP-joint tensor
+// BatchNorm, stsgcn.py:187-199 at stsae_unet.py:381-394) and ADDS the VUP-joint result to the U-Net skip tensor in place
 template <int T_, int V_, int CIN_, int COUT_, int NW_, int VUP_ = 0>
 struct CfCfg {
   using Mix = TcCfg<T_, V_, COUT_, COUT_, NW_>;  // task shapes of the two mixes (they depend on T, V and the window count only)
   static constexpr int T = T_, V = V_, CIN = CIN_, COUT = COUT_, NW = NW_, VUP = VUP_;
   using Up = std::conditional_t<(VUP_ > 0), ResampleParams<V_, (VUP_ > 0 ? VUP_ : 1)>, CfNoUp>;
   // fused resample: an epilogue thread owns UP_WG output joints (g, g + UP_NG, ...) of the frames fg, fg + UP_FG, ... of the tile
-  static constexpr int UP_WG = 3;
+  // (12 output joints: 4 groups of 3 x 24 frames = 96 threads, one round; 17: 5 groups of 4 x 24 = 120 threads, one round)
+  static constexpr int UP_WG = VUP_ > 12 ? 4 : 3;
   static constexpr int UP_NG = (VUP_ + UP_WG - 1) / UP_WG;
   static constexpr int FRAMES = NW_ * T_;
   static constexpr int UP_FG = VUP_ > 0 ? ((kTcEpilogue / (UP_NG > 0 ? UP_NG : 1)) < FRAMES ? (kTcEpilogue / (UP_NG > 0 ? UP_NG : 1)) : FRAMES) : 1;
@@ -517,98 +518,57 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_cf_kernel(const Blo
     };
 
     // Fused CNN_layer + skip add (VUP > 0): the chunk's block outputs sit in Y2 slot s (written in place by final_stage);
-    //   out[n, c, t, w] = b[w] + sum_v W[w][v] * y[n, c, t, v] + skip[n, c, t, w]        (same operation order as
-    // joint_resample_kernel, so the fused and the stand-alone path agree bit for bit).  A thread owns the output joints
-    // g, g + UP_NG, ... of frames fg, fg + UP_FG, ...: consecutive threads store consecutive 16-byte elements.
-    // Work items of a chunk: k = round * C4 + c4 (frame f = fg + round * UP_FG, 4-channel plane c4).  The skip loads run two
-    // items ahead of the arithmetic (global latency ~800 cycles against ~300 cycles of work per item), the first two are
-    // issued before the drain of the next Z chunk.
-    constexpr int UPW = VUP > 0 ? Cfg::UP_WG : 1;
-    struct UpSkip { float4 a[UPW], b[UPW]; };
+    //   out[n, c, t, w] = skip[n, c, t, w] + (b[w] + sum_v W[w][v] * y[n, c, t, v])
+    // The skip tensor is not loaded: `out` IS the skip buffer (its last use in the U-Net) and the resampled value is added
+    // to it in L2 with a vector reduction (red.global.add.v4.f32: fire and forget, one per 16-byte element, so the result is
+    // the same single rounding as the stand-alone kernel's a + skip and does not depend on timing).  Loading the skip values
+    // into registers instead cost two thirds of this stage (by elimination: 41.8 -> 32.3 ms per step without the loads).
+    // A thread owns the output joints g, g + UP_NG, ... of frames fg, fg + UP_FG, ...: consecutive threads touch consecutive
+    // 16-byte elements.  Work items of a chunk: k = round * C4 + c4 (frame f = fg + round * UP_FG, 4-channel plane c4).
     const int up_fg = etid / (VUP > 0 ? Cfg::UP_NG : 1), up_g = etid - up_fg * (VUP > 0 ? Cfg::UP_NG : 1);
-    auto up_item = [&](int it, int k, int64_t& o0) -> bool {  // global offset of (frame, plane, joint g); false: nothing to do
-      const int ti = it / NCH2, c = it - ti * NCH2;
-      const int64_t tile = blockIdx.x + int64_t(ti) * gridDim.x;
-      const int f = up_fg + (k / C4) * Cfg::UP_FG, c4 = k % C4;
-      const int wl = f / T, t = f - wl * T;
-      const int64_t wdw = tile * NW + wl;
-      o0 = act_off(wdw, c * 4 + c4, t * VUP + up_g, COUT, T * VUP);
-      return up_fg < Cfg::UP_FG && f < Cfg::FRAMES && wdw < io.n;
-    };
-    auto up_load = [&](int it, int k, float4* sk) {
-      int64_t o0;
-      if (up_item(it, k, o0)) {
-#pragma unroll
-        for (int j = 0; j < UPW; ++j)
-          if (up_g + j * Cfg::UP_NG < VUP) sk[j] = ldg_nc4(io.skip + o0 + int64_t(j) * Cfg::UP_NG * 4);
-      }
-    };
-    auto up_begin = [&](int it, UpSkip& st) {
-      if constexpr (VUP > 0) {
-        up_load(it, 0, st.a);
-        up_load(it, 1, st.b);
-        // The skip tensor was written several kernels ago and comes from HBM; its loads are two thirds of this stage's cost
-        // (by elimination: 41.8 -> 32.3 ms per step without them).  Pull the NEXT chunk's rows into L2 now, a whole chunk period
-        // ahead: the register loads then see L2 latency, which the two-item look-ahead covers better (43.3 -> 42.0 ms).
-        // (Requesting all of a chunk's skip values into registers before the drain measured slower: 50.9 ms.)
-        if (it + 1 < npairs2) {
-#pragma unroll
-          for (int k = 0; k < Cfg::UP_ROUNDS * C4; ++k) {
-            int64_t o0;
-            if (up_item(it + 1, k, o0)) {
-#pragma unroll
-              for (int j = 0; j < UPW; ++j)
-                if (up_g + j * Cfg::UP_NG < VUP)
-                  asm volatile("prefetch.global.L2 [%0];" ::"l"(io.skip + o0 + int64_t(j) * Cfg::UP_NG * 4));
-            }
-          }
-        }
-      }
-    };
-    auto up_finish = [&](int it, UpSkip& st) {
+    auto upsample = [&](int it) {
       if constexpr (VUP > 0) {
         constexpr int WG = Cfg::UP_WG, NG = Cfg::UP_NG, K = Cfg::UP_ROUNDS * C4;
-        static_assert(K % 2 == 0, "items are processed in pairs");
-        const int s = it & 1;
+        const int ti = it / NCH2, c = it - ti * NCH2, s = it & 1;
+        const int64_t tile = blockIdx.x + int64_t(ti) * gridDim.x;
         named_bar_sync(3, kTcEpilogue);  // every row of the chunk is in place
-        float rw[WG][V], rb[WG];
+        if (up_fg < Cfg::UP_FG) {
+          float rw[WG][V], rb[WG];
 #pragma unroll
-        for (int j = 0; j < WG; ++j) {
-          const float* wp = smem + Cfg::SM_UP + (up_g + j * NG < VUP ? up_g + j * NG : 0) * (V + 1);
-          rb[j] = wp[V];
+          for (int j = 0; j < WG; ++j) {
+            const float* wp = smem + Cfg::SM_UP + (up_g + j * NG < VUP ? up_g + j * NG : 0) * (V + 1);
+            rb[j] = wp[V];
 #pragma unroll
-          for (int v = 0; v < V; ++v) rw[j][v] = wp[v];
-        }
-        const float* y2 = sY2 + s * ARR;
-        auto compute = [&](int k, const float4* sk) {
-          int64_t o0;
-          if (!up_item(it, k, o0)) return;
-          const int f = up_fg + (k / C4) * Cfg::UP_FG, c4 = k % C4;
-          float4 a[WG];
-#pragma unroll
-          for (int j = 0; j < WG; ++j) a[j] = make_float4(rb[j], rb[j], rb[j], rb[j]);
-          const float* xp = y2 + (c4 * ROWS + f * V) * 4;
-#pragma unroll
-          for (int v = 0; v < V; ++v) {
-            const float4 x = *reinterpret_cast<const float4*>(xp + v * 4);
-#pragma unroll
-            for (int j = 0; j < WG; ++j) {
-              a[j].x = fmaf(rw[j][v], x.x, a[j].x); a[j].y = fmaf(rw[j][v], x.y, a[j].y);
-              a[j].z = fmaf(rw[j][v], x.z, a[j].z); a[j].w = fmaf(rw[j][v], x.w, a[j].w);
-            }
+            for (int v = 0; v < V; ++v) rw[j][v] = wp[v];
           }
-#pragma unroll
-          for (int j = 0; j < WG; ++j)
-            if (up_g + j * NG < VUP)
-              stg4_pred(io.out + o0 + int64_t(j) * NG * 4,
-                        make_float4(a[j].x + sk[j].x, a[j].y + sk[j].y, a[j].z + sk[j].z, a[j].w + sk[j].w), true);
-        };
+          const float* y2 = sY2 + s * ARR;
 #pragma unroll 1
-        for (int k = 0; k < K; k += 2) {
-          compute(k, st.a);
-          if (k + 2 < K) up_load(it, k + 2, st.a);
-          compute(k + 1, st.b);
-          if (k + 3 < K) up_load(it, k + 3, st.b);
+          for (int k = 0; k < K; ++k) {
+            const int f = up_fg + (k / C4) * Cfg::UP_FG, c4 = k % C4;
+            const int wl = f / T, t = f - wl * T;
+            const int64_t wdw = tile * NW + wl;
+            if (f >= Cfg::FRAMES || wdw >= io.n) continue;
+            float4 a[WG];
+#pragma unroll
+            for (int j = 0; j < WG; ++j) a[j] = make_float4(rb[j], rb[j], rb[j], rb[j]);
+            const float* xp = y2 + (c4 * ROWS + f * V) * 4;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              const float4 x = *reinterpret_cast<const float4*>(xp + v * 4);
+#pragma unroll
+              for (int j = 0; j < WG; ++j) {
+                a[j].x = fmaf(rw[j][v], x.x, a[j].x); a[j].y = fmaf(rw[j][v], x.y, a[j].y);
+                a[j].z = fmaf(rw[j][v], x.z, a[j].z); a[j].w = fmaf(rw[j][v], x.w, a[j].w);
+              }
+            }
+            float* op = io.out + act_off(wdw, c * 4 + c4, t * VUP + up_g, COUT, T * VUP);
+#pragma unroll
+            for (int j = 0; j < WG; ++j)
+              if (up_g + j * NG < VUP)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op + j * NG * 4), "f"(a[j].x), "f"(a[j].y),
+                             "f"(a[j].z), "f"(a[j].w)
+                             : "memory");
+          }
         }
         mbar_arrive(BAR(CF_Y2_EMPTY + s));
       }
@@ -630,10 +590,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) stgcn_block_cf_kernel(const Blo
       // refill the Z slot this chunk's mixes released (the A-mix of `it` is done, hence its T-mix; NZ = 2 = the Y2 ring depth, so
       // slot (it + NZ) % NZ is the one iteration `it` used) -- possibly with the first chunks of the next tile, whose
       // convolution ran on the tensor pipe meanwhile
-      UpSkip st;
-      up_begin(it, st);
       if (it + Cfg::NZ < npairs2) drain(it + Cfg::NZ);
-      up_finish(it, st);  // (after the drain: the T-mix warps get their next chunk first)
+      upsample(it);  // (after the drain: the T-mix warps get their next chunk first)
     }
   }
 

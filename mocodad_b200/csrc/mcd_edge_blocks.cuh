@@ -8,7 +8,9 @@
 // re-association changes results by rounding only (parity tests: 2e-5 against the reference per layer).
 //
 // One thread per (window of the tile, position (t, v)); the 2-channel planes pass through shared memory between
-// the T-mix and the A-mix; the mix matrices are read through the read-only L1 path.
+// the T-mix and the A-mix.  A thread's mix weights (column (t -> tq) of T[vw], column (v -> vw) of A[tq]: T + V values) do
+// not depend on the tile, so the persistent loop keeps them in registers -- read through L1 per tile they were a third of the
+// kernel's L1/shared-memory wavefronts, the pipe ncu shows at 80 % (profiles/r02_ncu_summary.txt).
 #pragma once
 #include "mcd_kernels.cuh"
 
@@ -27,10 +29,14 @@ struct EdgeCfg {
   static constexpr int TP4 = (T + 3) / 4 * 4;
   static constexpr int TMS = T * TP4 + 4;
   static_assert(THREADS <= 1024, "tile too large");
+  // mix weights in registers (T + V per thread) -- except in the last block at long windows, whose convolution prologue and
+  // fused DDPM update need the registers and the third resident CTA more (measured at T=24: 9.5 -> 10.3 ms per step with them)
+  static constexpr bool REG_W = HEAD || T < 12;
+  static constexpr int MIN_CTAS = (REG_W && T >= 12) ? 2 : 3;  // resident CTAs per SM the register budget is held to
 };
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS) edge_block_kernel(const BlockWeights wt, const BlockIO io) {
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) edge_block_kernel(const BlockWeights wt, const BlockIO io) {
   constexpr int T = Cfg::T, V = Cfg::V, P = Cfg::P, ROWS = Cfg::ROWS, NW = Cfg::NW;
   constexpr int VP = Cfg::VP, CW = Cfg::CW, CE = Cfg::CE;
   constexpr bool HEAD = Cfg::HEAD;
@@ -62,6 +68,16 @@ __global__ void __launch_bounds__(Cfg::THREADS) edge_block_kernel(const BlockWei
   const int p = tid - wl * P;
   const int tq = p / V, vw = p - tq * V;  // this thread's (frame, joint)
   const float slope = wt.prelu;
+  constexpr bool REG_W = Cfg::REG_W;
+  const float* tp = wt.TmE + tq * V + vw;  // [t][q][v]: the lanes of a warp (consecutive joints) read one contiguous span
+  const float* ap = wt.A + tq * V * VP + vw;
+  float wT[REG_W ? T : 1], wA[REG_W ? V : 1];
+  if constexpr (REG_W) {
+#pragma unroll
+    for (int t = 0; t < T; ++t) wT[t] = live ? __ldg(tp + t * T * V) : 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) wA[v] = live ? __ldg(ap + v * VP) : 0.f;
+  }
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t w = tile * NW + wl;
@@ -107,11 +123,10 @@ __global__ void __launch_bounds__(Cfg::THREADS) edge_block_kernel(const BlockWei
     // T-mix: y1[c][q][v] = sum_t s0[c][t][v] * Tm[v][t][q]      (this thread: q = tq, v = vw)        stsgcn.py:154
     if (live) {
       float a0 = 0.f, a1 = 0.f;
-      const float* tp = wt.TmE + tq * V + vw;  // [t][q][v]: the lanes of a warp (consecutive joints) read one contiguous span
       const int base = wl * P + vw;
 #pragma unroll
       for (int t = 0; t < T; ++t) {
-        const float k = __ldg(tp + t * T * V);
+        const float k = REG_W ? wT[REG_W ? t : 0] : __ldg(tp + t * T * V);
         a0 = fmaf(s0[0][base + t * V], k, a0);
         a1 = fmaf(s0[1][base + t * V], k, a1);
       }
@@ -123,11 +138,10 @@ __global__ void __launch_bounds__(Cfg::THREADS) edge_block_kernel(const BlockWei
     // A-mix: y2[c][t][w] = sum_v s1[c][t][v] * A[t][v][w]       (this thread: t = tq, w = vw)        stsgcn.py:155
     if (live) {
       float m0 = 0.f, m1 = 0.f;
-      const float* ap = wt.A + tq * V * VP + vw;
       const int base = wl * P + tq * V;
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        const float k = __ldg(ap + v * VP);
+        const float k = REG_W ? wA[REG_W ? v : 0] : __ldg(ap + v * VP);
         m0 = fmaf(s1[0][base + v], k, m0);
         m1 = fmaf(s1[1][base + v], k, m1);
       }

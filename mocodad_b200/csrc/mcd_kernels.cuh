@@ -132,7 +132,8 @@ struct BlockIO {
   // element is read and written by the same thread) instead of eps; saves the round trip of eps through HBM and a launch
   int32_t fuse_ddpm;
   DdpmArgs ddpm;
-  // conv-first blocks with the fused up-path CNN_layer (mcd_block_cf.cuh, CfCfg::VUP > 0): the U-Net skip tensor, same shape as `out`
+  // conv-first blocks with the fused up-path CNN_layer (mcd_block_cf.cuh, CfCfg::VUP > 0): the U-Net skip tensor -- must be
+  // `out` itself: the resampled block output is accumulated onto it in place
   const float* skip;
 };
 
