@@ -97,6 +97,9 @@ struct PackedBlock {
   int cin = 0, cout = 0, V = 0, T = 0;
   bool emb = false, resconv = false;
   BlockWeights w{};
+  // host copies of the folded 1x1 convolutions [k][cout] and bias of the 2-channel-sided (edge) blocks: their kernel takes them as a
+  // parameter (constant bank)
+  std::vector<float> hW, hWr, hbias;
 };
 struct PackedResample {
   int vin = 0, vout = 0;
@@ -322,9 +325,19 @@ int edge_block_op(int action, const mcd_model* m, int slot, const BlockWeights* 
   }
   const int64_t cap = int64_t(m->num_sms) * per_sm;
   const int grid = int(ntiles < cap ? ntiles : cap);
+  const PackedBlock& pb = m->unet[slot - SLOT_UNET0];
+  if (pb.hW.size() != size_t(HEAD ? 4 : 32) * (HEAD ? 16 : 2) || pb.hWr.size() != pb.hW.size() || pb.hbias.size() != size_t(Cfg::CE))
+    return fail(MCD_ERR_UNSUPPORTED, "block %s was not packed for the edge kernel", kSlotNames[slot]);
+  EdgeConst<Cfg::CW, Cfg::CE> ec;
+  for (int which = 0; which < 2; ++which) {
+    const std::vector<float>& src = which == 0 ? pb.hW : pb.hWr;
+    for (int a = 0; a < Cfg::CW; ++a)
+      for (int b = 0; b < 2; ++b) ec.w[which][a][b] = HEAD ? src[size_t(b) * 16 + a] : src[size_t(a) * 2 + b];  // HEAD: [co][k], TAIL: [k][c']
+  }
+  for (int i = 0; i < Cfg::CE; ++i) ec.bias[i] = pb.hbias[i];
   {
     LaunchScope ls(m, slot, io->n, s);
-    edge_block_kernel<Cfg><<<grid, Cfg::THREADS, 0, s>>>(*w, *io);
+    edge_block_kernel<Cfg><<<grid, Cfg::THREADS, 0, s>>>(*w, *io, ec);
   }
   return check_launch(kSlotNames[slot]);
 }
@@ -808,6 +821,11 @@ bool pack_block(const mcd_model* m, Arena* ar, const std::string& p, int cin, in
     for (int co = 0; co < cout; ++co) ar->h[off->bE + co] = (*bE)[co];
   }
   pb->w.prelu = (*pr)[0];
+  if (cin <= 2 || cout <= 2) {
+    pb->hW.assign(ar->h.begin() + off->W, ar->h.begin() + off->W + size_t(cinp) * cout);
+    if (pb->resconv) pb->hWr.assign(ar->h.begin() + off->Wr, ar->h.begin() + off->Wr + size_t(cinp) * cout);
+    pb->hbias.assign(ar->h.begin() + off->bias, ar->h.begin() + off->bias + cout);
+  }
   // tensor-core operands (mcd_block_tc.cuh): per 16-channel chunk, parts [W hi | W lo | Wr hi | Wr lo], each
   // [COUT rows][16 k] fp32 with the 16-byte chunk index XORed by bits 1..2 of the row (UMMA SWIZZLE_64B, K-major).
   off->has_bop = (cin % 16 == 0) && (cout % 32 == 0);

@@ -35,33 +35,26 @@ struct EdgeCfg {
   static constexpr int MIN_CTAS = (REG_W && T >= 12) ? 2 : 3;  // resident CTAs per SM the register budget is held to
 };
 
+// The block's folded 1x1 convolutions and bias travel as a kernel parameter: every use has a compile-time index, so the
+// values are constant-bank operands of the FMAs instead of broadcast shared-memory loads (they were half of the kernel's
+// LSU instructions: 96 of 178 per thread and tile in the first block, 128 of 210 in the last).
+template <int CW, int CE>
+struct EdgeConst {
+  float w[2][CW][2];  // TAIL: [conv | residual conv][k][c']   HEAD: [conv | residual conv][co][k]
+  float bias[CE];
+};
+
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) edge_block_kernel(const BlockWeights wt, const BlockIO io) {
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) edge_block_kernel(const BlockWeights wt, const BlockIO io,
+                                                                                 const __grid_constant__ EdgeConst<Cfg::CW, Cfg::CE> ec) {
   constexpr int T = Cfg::T, V = Cfg::V, P = Cfg::P, ROWS = Cfg::ROWS, NW = Cfg::NW;
   constexpr int VP = Cfg::VP, CW = Cfg::CW, CE = Cfg::CE;
   constexpr bool HEAD = Cfg::HEAD;
   __shared__ float s0[2][ROWS];       // mix input  (2 channels)
   __shared__ float s1[2][ROWS];       // after the T-mix
   __shared__ float sEmb[NW][CE];      // Linear(SiLU(pos + cond)) of the tile's windows
-  __shared__ float sW[2][CW][2];      // TAIL: [conv | residual conv][k][c']   HEAD: [conv | residual conv][co][k]
-  __shared__ float sBias[CE];
 
   const int tid = threadIdx.x;
-  // folded weights: Wt / Wrt are stored [k][cout] (k padded to 4 for the head)
-  for (int i = tid; i < 2 * CW * 2; i += Cfg::THREADS) {
-    const int which = i / (CW * 2), rem = i - which * CW * 2;
-    const float* src = which == 0 ? wt.Wt : wt.Wrt;
-    if constexpr (HEAD) {
-      const int co = rem / 2, k = rem - co * 2;
-      sW[which][co][k] = src[k * 16 + co];
-    } else {
-      const int k = rem / 2, c = rem - k * 2;
-      sW[which][k][c] = src[k * 2 + c];
-    }
-  }
-  for (int i = tid; i < CE; i += Cfg::THREADS) sBias[i] = wt.bias[i];
-  __syncthreads();
-
   const int64_t ntiles = (io.n + NW - 1) / NW;
   const bool live = tid < ROWS;
   const int wl = live ? tid / P : 0;
@@ -99,10 +92,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) edge_block_kernel
           for (int kk = 0; kk < 4; ++kk) {
             const float xk = f4get(xv, kk);
             const int k = g * 4 + kk;
-            u0 = fmaf(sW[0][k][0], xk, u0);
-            u1 = fmaf(sW[0][k][1], xk, u1);
-            x0 = fmaf(sW[1][k][0], xk, x0);
-            x1 = fmaf(sW[1][k][1], xk, x1);
+            u0 = fmaf(ec.w[0][k][0], xk, u0);
+            u1 = fmaf(ec.w[0][k][1], xk, u1);
+            x0 = fmaf(ec.w[1][k][0], xk, x0);
+            x1 = fmaf(ec.w[1][k][1], xk, x1);
           }
         }
         s0[0][tid] = u0;
@@ -153,18 +146,18 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) edge_block_kernel
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
               const int co = g * 4 + jj;
-              float v = sBias[co];
-              v = fmaf(sW[0][co][0], m0, v);
-              v = fmaf(sW[0][co][1], m1, v);
-              v = fmaf(sW[1][co][0], x0, v);
-              v = fmaf(sW[1][co][1], x1, v);
+              float v = ec.bias[co];
+              v = fmaf(ec.w[0][co][0], m0, v);
+              v = fmaf(ec.w[0][co][1], m1, v);
+              v = fmaf(ec.w[1][co][0], x0, v);
+              v = fmaf(ec.w[1][co][1], x1, v);
               v = v > 0.f ? v : slope * v;
               o[jj] = v + sEmb[wl][co];
             }
             *reinterpret_cast<float4*>(io.out + act_off(w, g, p, 16, P)) = make_float4(o[0], o[1], o[2], o[3]);
           }
         } else {  // + residual conv, PReLU, + emb, + the U-Net's outer residual -> reference layout [n][2][P]
-          float v0 = m0 + x0 + sBias[0], v1 = m1 + x1 + sBias[1];
+          float v0 = m0 + x0 + ec.bias[0], v1 = m1 + x1 + ec.bias[1];
           v0 = (v0 > 0.f ? v0 : slope * v0) + sEmb[wl][0];
           v1 = (v1 > 0.f ? v1 : slope * v1) + sEmb[wl][1];
           const int64_t e0 = (w * 2) * P + p;
