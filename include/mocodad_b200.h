@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 4
+#define MCD_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define MCD_API __attribute__((visibility("default")))
@@ -183,6 +183,18 @@ MCD_API int mcd_build_items(const mcd_model* m, const float* d_rows, int64_t F, 
  * (may be NULL) the running min / max over samples ('best' / 'worst' strategies). */
 MCD_API int mcd_window_loss(const mcd_model* m, const float* d_x0, const float* d_data, int64_t B,
                     int32_t G, float* d_losses, float* d_best, float* d_worst, void* stream);
+
+/* ---- f2: score assembly, first stage -- MoCoDAD.post_processing, models/mocodad.py:386-391 over
+ * compute_var_matrix (utils/eval_utils.py:27-34) + nanmax: every window spreads its loss over the seg_len frames it covers and
+ * a frame of a (transformation, scene, clip, person) row keeps the MAXIMUM over the windows that contain it; frames never covered
+ * stay 0.  d_loss [N] float32; d_frames [N, seg_len] int64, 1-based frame numbers (0 wraps to the row's last frame, like the
+ * reference's numpy index -1); d_row [N] int64 = the window's output row (< 0: skip the window); d_row_len [rows] int32 = frame
+ * count of the row's clip; d_out [rows, stride] float32, zero-filled by the call.  Bit-identical to the reference's values
+ * (a maximum has no rounding).  Needs only the handle's device (no weights).  The rest of the tail (padding around absences,
+ * mean + log-range mix over persons, shift + Gaussian filter, roc_auc_score) stays on the host: mocodad_b200/postproc.py. */
+MCD_API int mcd_frame_scores(const mcd_model* m, const float* d_loss, const int64_t* d_frames, const int64_t* d_row,
+                     const int32_t* d_row_len, int64_t N, int32_t seg_len, int64_t rows, int64_t stride, float* d_out,
+                     void* stream);
 
 /* ---- the hot loop: the body of MoCoDAD.forward, mocodad.py:129-184 --------------------------
  * For each of G samples: x_T, then for t = N-1..1 denoise + DDPM update; then per-window losses.

@@ -28,7 +28,7 @@ class McdConfig(C.Structure):
 
 
 MCD_OK = 0
-ABI_VERSION = 4   # MCD_ABI_VERSION in include/mocodad_b200.h
+ABI_VERSION = 5   # MCD_ABI_VERSION in include/mocodad_b200.h
 STATUS_NAMES = {0: "MCD_OK", -1: "MCD_ERR_INVALID_ARG", -2: "MCD_ERR_UNSUPPORTED",
                 -3: "MCD_ERR_NOT_FINALIZED", -4: "MCD_ERR_MISSING_TENSOR", -5: "MCD_ERR_CUDA",
                 -6: "MCD_ERR_WORKSPACE"}
@@ -63,6 +63,8 @@ SIGNATURES = {
                                        C.c_void_p]),
     "mcd_build_items": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, c_double_p, c_double_p,
                                   c_float_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "mcd_frame_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64,
+                                   C.c_int64, C.c_void_p, C.c_void_p]),
     "mcd_window_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
     "mcd_reverse_diffusion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_uint64,

@@ -79,6 +79,7 @@ enum Slot {
   SLOT_ITEMS,                           // window ingest: frame rows -> robust-scaled, transformed dataset items
   SLOT_LATENT,                          // latent variant: the MLP denoiser + DDPM loop on latent vectors (unit: vectors)
   SLOT_TTD,                             // latent variant: to_time_dim, the linear map onto the latent space
+  SLOT_FSCORE,                          // score assembly: per-(clip, person) frame maxima over windows (unit: windows)
   SLOT_COUNT
 };
 const char* kSlotNames[SLOT_COUNT] = {
@@ -87,7 +88,7 @@ const char* kSlotNames[SLOT_COUNT] = {
     "down2",         "up3",          "up2",          "ddpm_step",    "randn",        "window_loss",
     "best_worst",    "cond.enc0",    "cond.enc1",    "cond.enc2",    "cond.enc3",    "cond.btlnk",
     "tap_transpose", "time_embedding", "expand_transforms", "normalize_frames", "build_items",
-    "latent_diffusion", "latent.to_time_dim"};
+    "latent_diffusion", "latent.to_time_dim", "frame_scores"};
 
 constexpr int nw_for(int T, int V0) {  // windows per CTA tile: ~408 (frame,joint) rows at the widest level
   return (408 / (T * V0)) > 0 ? 408 / (T * V0) : 1;
@@ -1439,6 +1440,23 @@ int mcd_build_items(const mcd_model* m, const float* d_rows, int64_t F, const in
   return check_launch("build_items");
 }
 
+int mcd_frame_scores(const mcd_model* m, const float* d_loss, const int64_t* d_frames, const int64_t* d_row, const int32_t* d_row_len,
+                     int64_t N, int32_t seg_len, int64_t rows, int64_t stride, float* d_out, void* stream) {
+  MCD_TRY(check_created(m));
+  if (N < 0 || seg_len < 1 || rows < 0 || stride < 1 || d_out == nullptr || (N > 0 && (d_loss == nullptr || d_frames == nullptr || d_row == nullptr)) ||
+      (rows > 0 && d_row_len == nullptr))
+    return fail(MCD_ERR_INVALID_ARG, "mcd_frame_scores: bad argument");
+  CUDA_TRY(cudaSetDevice(m->cfg.device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (rows > 0) CUDA_TRY(cudaMemsetAsync(d_out, 0, size_t(rows) * stride * sizeof(float), s));
+  if (N == 0 || rows == 0) return MCD_OK;
+  {
+    LaunchScope ls(m, SLOT_FSCORE, N, s);
+    frame_scores_kernel<<<grid_for(N * seg_len, kThreads, m->num_sms, 8), kThreads, 0, s>>>(d_loss, d_frames, d_row, d_row_len, N, seg_len, stride, d_out);
+  }
+  return check_launch("frame_scores");
+}
+
 int mcd_window_loss(const mcd_model* m, const float* d_x0, const float* d_data, int64_t B, int32_t G, float* d_losses,
                     float* d_best, float* d_worst, void* stream) {
   MCD_TRY(check_ready(m));
@@ -1755,6 +1773,8 @@ int mcd_profile_slot_cost(const mcd_model* m, int slot, double* bytes_per_window
   } else if (slot == SLOT_ITEMS) {  // per item: n_frames rows read (L2-shared between items), [2, n_frames, 17] written
     bytes = 4.0 * 2 * m->cfg.n_frames * 17 * 2;
     flops = 10.0 * 2 * m->cfg.n_frames * 17;
+  } else if (slot == SLOT_FSCORE) {  // per window: loss + row id + n_frames frame numbers read, n_frames atomic maxima
+    bytes = 4.0 + 8.0 + 8.0 * m->cfg.n_frames + 4.0 * m->cfg.n_frames;
   } else if (slot == SLOT_EMB) {
     bytes = 4.0 * (m->E + m->ws_emb);
     flops = 2.0 * m->E * m->ws_emb;

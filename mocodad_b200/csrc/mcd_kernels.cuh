@@ -570,6 +570,30 @@ __global__ void __launch_bounds__(kRsFrames) joint_resample_kernel(const float* 
 }
 
 // ------------------------------------------------------------------------------------------
+// Score assembly, first stage (models/mocodad.py:386-391 over compute_var_matrix, utils/eval_utils.py:27-34): every window
+// spreads its loss over the frames it covers, and a frame of a (transformation, clip, person) row keeps the maximum over the
+// windows that contain it; frames never covered stay 0.  One thread per (window, frame of the window); the maximum of
+// non-negative floats is the maximum of their bit patterns as signed integers (negative losses lose against the 0 fill exactly
+// like numpy's maximum against the zero-initialised row), so atomicMax gives the reference's float32 values bit for bit,
+// in any order.  Frame numbers are 1-based; index -1 wraps to the row's last frame like numpy's fancy assignment.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) frame_scores_kernel(const float* __restrict__ loss, const int64_t* __restrict__ frames,
+                                                                const int64_t* __restrict__ row, const int32_t* __restrict__ row_len,
+                                                                int64_t n_items, int seg_len, int64_t stride, float* __restrict__ out) {
+  const int64_t total = n_items * seg_len;
+  for (int64_t i = blockIdx.x * int64_t(kThreads) + threadIdx.x; i < total; i += int64_t(gridDim.x) * kThreads) {
+    const int64_t n = i / seg_len;
+    const int64_t r = row[n];
+    if (r < 0) continue;  // window of a clip without ground truth: not scored
+    const int len = row_len[r];
+    int64_t f = frames[i] - 1;
+    if (f < 0) f += len;
+    if (f < 0 || f >= len || f >= stride) continue;
+    atomicMax(reinterpret_cast<int*>(out + r * stride + f), __float_as_int(loss[n]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Time / condition embedding of every denoiser block, for all windows of a launch:
 //   emb[w][off_b + co] = bE_b[co] + sum_j WE_b[co][j] * SiLU(pos_t[j] + cond[w][j])        stsgcn.py:112-114 (emb_layer),
 //   temb = pos_encoding(t) + cond_emb                                                      stsae_unet.py:425-426

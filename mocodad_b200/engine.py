@@ -187,6 +187,33 @@ class ScoringEngine:
                                            best.data_ptr(), worst.data_ptr(), self._stream()))
         return {"losses": losses, "best": best, "worst": worst}
 
+    def frame_scores(self, loss: torch.Tensor, frames: torch.Tensor, row: torch.Tensor, row_len: torch.Tensor,
+                     stride: int) -> torch.Tensor:
+        """Score assembly, first stage (mocodad.py:386-391 over utils/eval_utils.py:27-34): ``out[row[n], frames[n, k] - 1]`` =
+        max over the windows n that cover the frame of ``loss[n]`` (0 where no window does; frame number 0 wraps to the row's
+        last frame like the reference's numpy index).  ``row`` < 0 skips a window.  Returns float32 [rows, stride]."""
+        N, rows = loss.shape[0], row_len.shape[0]
+        for name, t, dt in (("loss", loss, torch.float32), ("frames", frames, torch.int64), ("row", row, torch.int64),
+                            ("row_len", row_len, torch.int32)):
+            if t.device != self.device or t.dtype != dt or not t.is_contiguous():
+                raise ValueError(f"{name}: need a contiguous {dt} tensor on the engine's device")
+        if frames.dim() != 2 or frames.shape[0] != N or row.shape != (N,) or loss.dim() != 1 or row_len.dim() != 1:
+            raise ValueError("frame_scores: loss [N], frames [N, seg_len], row [N], row_len [rows]")
+        out = self._new(rows, int(stride))
+        with torch.cuda.device(self.device):
+            check(self.lib.mcd_frame_scores(self._h, loss.data_ptr(), frames.data_ptr(), row.data_ptr(), row_len.data_ptr(), N,
+                                            int(frames.shape[1]), rows, int(stride), out.data_ptr(), self._stream()))
+        return out
+
+    def frame_scores_host(self, loss: np.ndarray, frames: np.ndarray, row: np.ndarray, row_len: np.ndarray, stride: int) -> np.ndarray:
+        """``frame_scores`` on host arrays (the form ``postproc.dataset_auc`` hands over at the end of a test epoch)."""
+        dev = self.device
+        f = np.ascontiguousarray(frames, dtype=np.int64).reshape(len(loss), -1)
+        out = self.frame_scores(torch.from_numpy(np.ascontiguousarray(loss, dtype=np.float32)).to(dev),
+                                torch.from_numpy(f).to(dev), torch.from_numpy(np.ascontiguousarray(row, dtype=np.int64)).to(dev),
+                                torch.from_numpy(np.ascontiguousarray(row_len, dtype=np.int32)).to(dev), stride)
+        return out.cpu().numpy()
+
     # ------------------------------------------------------------------ the hot loop
     def reverse_diffusion(self, data: torch.Tensor, n_generated_samples: int, *, noise: Optional[torch.Tensor] = None,
                           seed: int = 0, first_window: int = 0, want_losses: bool = False, want_worst: bool = False,

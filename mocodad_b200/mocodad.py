@@ -354,8 +354,11 @@ class MoCoDAD(_Base):
     def post_processing(self, out, gt_data, trans, meta, frames) -> float:
         """Score assembly -> frame-level AUC (mocodad.py:337-430): per clip / person max over windows, padding around
         absences, log-range mix over persons, HR masks, shift + Gaussian smoothing, mean over the affine
-        transformations, ``roc_auc_score``.  Host-side numpy (mocodad_b200/postproc.py), pinned against the reference."""
+        transformations, ``roc_auc_score`` (mocodad_b200/postproc.py, pinned against the reference).  On a CUDA device the
+        first stage -- the per-(clip, person) frame maxima over the epoch's windows -- runs on the GPU (``mcd_frame_scores``);
+        the saved-tensor branch of a module that was never moved to a GPU assembles them on the host."""
         from . import postproc
+        accel = self.engine().frame_scores_host if self.device.type == "cuda" else None
         gt = postproc.load_ground_truth(self.gt_path)
         clip_masks = postproc.hr_ubnormal_masks(self.split) if (self.use_hr and self.dataset_name == 'UBnormal') else None
         avenue = postproc.avenue_hr_mask() if self.dataset_name == 'HR-Avenue' else None
@@ -363,7 +366,7 @@ class MoCoDAD(_Base):
                                           num_transform=self.num_transforms, pad_size=self.anomaly_score_pad_size,
                                           frames_shift=self.anomaly_score_frames_shift,
                                           filter_kernel_size=self.anomaly_score_filter_kernel_size,
-                                          clip_masks=clip_masks, avenue_masks=avenue))
+                                          clip_masks=clip_masks, avenue_masks=avenue, frame_scores=accel))
 
     def test_on_saved_tensors(self, split_name: str) -> float:
         """mocodad.py:433-448"""

@@ -33,6 +33,8 @@ def person_frame_scores(loss: np.ndarray, frames: np.ndarray, n_frames: int) -> 
     frame keeps the maximum over the windows that contain it; frames never covered stay 0
     (compute_var_matrix + nanmax, mocodad.py:390-391)."""
     out = np.zeros(n_frames, dtype=np.float64)
+    if len(loss) == 0:
+        return out
     idx = (np.asarray(frames, dtype=np.int64) - 1).reshape(len(loss), -1)  # frame numbers are 1-based
     # numpy fancy assignment (the reference's pose[n, frames-1] = loss[n]) wraps negative indices
     idx = np.where(idx < 0, idx + n_frames, idx)
@@ -88,7 +90,11 @@ def clip_scores(out: np.ndarray, meta: np.ndarray, frames: np.ndarray, gt: np.nd
         if pad_size != -1:
             s = pad_absences(s, n_frames, pad_size)
         per_person.append(s)
-    ps = np.stack(per_person, axis=0)
+    return mix_persons(np.stack(per_person, axis=0))
+
+
+def mix_persons(ps: np.ndarray) -> np.ndarray:
+    """mean + (max - min of log1p) over the persons of a clip (mocodad.py:393-401); ``ps`` [persons, frames] float64."""
     logs = np.log1p(ps)
     return ps.mean(axis=0) + (logs.max(axis=0) - logs.min(axis=0))
 
@@ -98,10 +104,14 @@ def dataset_auc(out: np.ndarray, trans: np.ndarray, meta: np.ndarray, frames: np
                 frames_shift: int, filter_kernel_size: float,
                 clip_masks: Optional[Dict[Tuple[int, int], np.ndarray]] = None,
                 avenue_masks: Optional[Dict[int, np.ndarray]] = None,
-                return_scores: bool = False):
+                return_scores: bool = False, frame_scores=None):
     """mocodad.py:337-430 with the ground truth passed as a dict {(scene, clip): 0/1 per frame}, visited in the
     reference's order (sorted file names ``{scene:02d}_{clip:04d}.npy`` == sorted (scene, clip) for zero-padded
-    names).  ``clip_masks`` are the HR-UBnormal boolean masks, ``avenue_masks`` the HR-Avenue keep masks."""
+    names).  ``clip_masks`` are the HR-UBnormal boolean masks, ``avenue_masks`` the HR-Avenue keep masks.
+
+    ``frame_scores``: optional accelerator for the first stage -- a callable ``(loss [N], frames [N, L], row [N], row_len [rows],
+    stride) -> float32 [rows, stride]`` with the semantics of ``person_frame_scores`` per row (``ScoringEngine.frame_scores_host``
+    = the CUDA kernel behind ``mcd_frame_scores``; a frame maximum has no rounding, so the AUC is the same to the last bit)."""
     from sklearn.metrics import roc_auc_score
     clip_masks = clip_masks or {}
     avenue_masks = avenue_masks or {}
@@ -114,12 +124,37 @@ def dataset_auc(out: np.ndarray, trans: np.ndarray, meta: np.ndarray, frames: np
     key = np.stack([trans.astype(np.int64), meta[:, 0].astype(np.int64), meta[:, 1].astype(np.int64)], axis=1)
     bounds = np.concatenate([[0], np.flatnonzero(np.any(key[1:] != key[:-1], axis=1)) + 1, [len(key)]]).astype(np.int64)
     groups = {tuple(key[b].tolist()): (int(b), int(e)) for b, e in zip(bounds[:-1], bounds[1:]) if e > b}
+    rows_of, row_scores = {}, None
+    if frame_scores is not None and len(out):
+        # one output row per (transformation, scene, clip, person) of a clip that has ground truth: consecutive in the sorted order
+        pkey = np.concatenate([key, meta[:, 2:3].astype(np.int64)], axis=1)
+        pb = np.concatenate([[0], np.flatnonzero(np.any(pkey[1:] != pkey[:-1], axis=1)) + 1, [len(pkey)]]).astype(np.int64)
+        row = np.full(len(out), -1, dtype=np.int64)
+        row_len: List[int] = []
+        for b, e in zip(pb[:-1], pb[1:]):
+            tr, scene, clip, _ = pkey[b].tolist()
+            gt = gt_by_clip.get((scene, clip))
+            if gt is None or tr >= num_transform:
+                continue
+            rows_of.setdefault((tr, scene, clip), []).append(len(row_len))
+            row[b:e] = len(row_len)
+            row_len.append(int(gt.shape[0]))
+        if row_len:
+            row_scores = np.asarray(frame_scores(out.astype(np.float32, copy=False), frames, row, np.asarray(row_len, dtype=np.int32),
+                                                 int(max(row_len))))
     per_transform, gt_all = [], None
     for tr in range(num_transform):
         scores, gts = [], []
         for (scene, clip), gt in gt_by_clip.items():
             lo, hi = groups.get((tr, int(scene), int(clip)), (0, 0))
-            s = clip_scores(out[lo:hi], meta[lo:hi], frames[lo:hi], gt, pad_size)
+            rws = rows_of.get((tr, int(scene), int(clip)))
+            if row_scores is not None and rws:
+                ps = row_scores[rws[0]:rws[-1] + 1, :gt.shape[0]].astype(np.float64)
+                if pad_size != -1:
+                    ps = np.stack([pad_absences(p, gt.shape[0], pad_size) for p in ps], axis=0)
+                s = mix_persons(ps)
+            else:
+                s = clip_scores(out[lo:hi], meta[lo:hi], frames[lo:hi], gt, pad_size)
             g = gt
             if (scene, clip) in clip_masks:
                 keep = clip_masks[(scene, clip)]

@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(_lib.SIGNATURES) == declared, "ctypes binding and header disagree"
-    assert lib.mcd_abi_version() == 4
+    assert lib.mcd_abi_version() == 5
 
 
 @pytest.mark.parametrize("N", [2, 10, 50, 1000])

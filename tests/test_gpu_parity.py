@@ -431,6 +431,45 @@ def test_layer_taps_with_many_tiles_per_cta_vs_oracle(T, n):
     assert torch.equal(got_eps, own + x)
 
 
+def test_frame_scores_kernel_vs_host_and_auc_bit_identity(golden):
+    """SURVEY.md 8 row f2, first stage on the device (mcd_frame_scores): per-row frame maxima over windows == the pinned host
+    restatement bit for bit (wrapping frame number 0, skipped rows, overlapping windows, empty rows), and the AUC through
+    ``dataset_auc`` with the kernel as accelerator == the all-host AUC exactly == the reference's."""
+    from mocodad_b200 import postproc, synthetic
+    eng, _ = _engine(6, 4)
+    rng = np.random.default_rng(5)
+    N, L, rows = 20000, 6, 37
+    row_len = rng.integers(8, 300, size=rows).astype(np.int32)
+    row_len[5] = 6
+    row = rng.integers(-1, rows, size=N).astype(np.int64)
+    row[row == 11] = 12                                   # row 11 stays empty
+    start = rng.integers(0, 10_000, size=N)
+    frames = np.empty((N, L), dtype=np.int64)
+    for n in range(N):
+        ln = int(row_len[max(row[n], 0)])
+        s0 = int(start[n] % max(ln - L + 1, 1))
+        frames[n] = np.arange(s0, s0 + L) + (1 if n % 50 else 0)   # every 50th window starts at frame number 0 (numpy index -1)
+    loss = rng.random(N, dtype=np.float32) * 3
+    loss[::97] = 0.0
+    got = eng.frame_scores_host(loss, frames, row, row_len, int(row_len.max()))
+    for r in range(rows):
+        sel = row == r
+        want = postproc.person_frame_scores(loss[sel], frames[sel], int(row_len[r])).astype(np.float32)
+        assert np.array_equal(got[r, :row_len[r]], want), r
+        assert not got[r, row_len[r]:].any()
+    assert not got[11].any()
+    # through the whole tail, on the fixture epochs the reference's AUCs are pinned on
+    ref = golden("postproc")
+    from test_postproc import CASES as PCASES
+    for name, (clips, dataset, pad, shift, ksize, ntr) in PCASES.items():
+        out, trans, meta, frames2, gt = synthetic.synth_scored_dataset(clips, num_transform=ntr)
+        kw = dict(num_transform=ntr, pad_size=pad, frames_shift=shift, filter_kernel_size=ksize,
+                  avenue_masks=postproc.avenue_hr_mask() if dataset == "HR-Avenue" else None)
+        host = postproc.dataset_auc(out, trans, meta, frames2, gt, **kw)
+        dev = postproc.dataset_auc(out, trans, meta, frames2, gt, frame_scores=eng.frame_scores_host, **kw)
+        assert host == dev and abs(dev - float(ref[name])) < 1e-9, name
+
+
 def test_seeded_torch_rng_on_cuda_reproduces_the_eager_reference_draws():
     """SURVEY.md 8 row a10, "identical inputs and seeds": with `b200_rng: torch` the module draws its noise with torch.randn on
     the CUDA generator in the reference's call order (mocodad.py:162,176), so under one torch.manual_seed it scores with exactly

@@ -23,6 +23,40 @@ def test_auc_matches_reference(golden, name):
     assert abs(auc - float(golden("postproc")[name])) < 1e-9
 
 
+def _frame_scores_host(loss, frames, row, row_len, stride):
+    """The contract of the ``frame_scores`` accelerator (mcd_frame_scores), restated with the pinned per-person function."""
+    frames = np.asarray(frames).reshape(len(loss), -1)
+    out = np.zeros((len(row_len), stride), dtype=np.float32)
+    for r in range(len(row_len)):
+        sel = np.asarray(row) == r
+        out[r, :row_len[r]] = postproc.person_frame_scores(np.asarray(loss)[sel], frames[sel], int(row_len[r]))
+    return out
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_auc_with_the_frame_score_accelerator_is_bit_identical(golden, name):
+    """Host logic of the accelerated first stage: row assignment per (transformation, scene, clip, person), clips without
+    windows or ground truth, padding on the accelerator's rows -- same scores to the last bit as the all-host path."""
+    clips, dataset, pad, shift, ksize, ntr = CASES[name]
+    out, trans, meta, frames, gt = synthetic.synth_scored_dataset(clips, num_transform=ntr)
+    # windows of a clip that has no ground truth file must be ignored by both paths
+    extra = slice(0, 7)
+    out = np.concatenate([out, out[extra]]); trans = np.concatenate([trans, trans[extra]])
+    m2 = meta[extra].copy(); m2[:, 1] = 9999
+    meta = np.concatenate([meta, m2]); frames = np.concatenate([frames, frames[extra]])
+    kw = dict(num_transform=ntr, pad_size=pad, frames_shift=shift, filter_kernel_size=ksize, return_scores=True,
+              avenue_masks=postproc.avenue_hr_mask() if dataset == "HR-Avenue" else None)
+    auc0, pds0, gt0 = postproc.dataset_auc(out, trans, meta, frames, gt, **kw)
+    calls = []
+
+    def accel(*a):
+        calls.append(a[3])
+        return _frame_scores_host(*a)
+    auc1, pds1, gt1 = postproc.dataset_auc(out, trans, meta, frames, gt, frame_scores=accel, **kw)
+    assert len(calls) == 1 and auc0 == auc1 and np.array_equal(pds0, pds1) and np.array_equal(gt0, gt1)
+    assert abs(auc1 - float(golden("postproc")[name])) < 1e-9
+
+
 def test_avenue_mask_lengths():
     m = postproc.avenue_hr_mask()
     assert {k: len(v) for k, v in m.items()} == {1: 1439, 2: 1211, 3: 923, 6: 1283, 16: 740}  # eval_utils.py:153-157
