@@ -48,7 +48,8 @@ def parse_args():
     p.add_argument("--no-shipped", action="store_true", help="skip the shipped-shape (T=3, B=1024 / 2048) sub-record")
     p.add_argument("--stress", action="store_true",
                    help="BASELINE.json configs[4]-style sweep (e.g. --batch 125000 --noise-steps 1000 --gen 1 on 8 GPUs): device-timed "
-                        "value only, warm-up on 1/32 of the batch, no e2e / baselines / per-kernel profile")
+                        "value only, warm-up on 1/32 of the batch, no e2e / baselines / per-kernel profile.  One step = one full sweep "
+                        "(~66 s at that size): pass --steps 1 unless an average over several sweeps is wanted")
     return p.parse_args()
 
 
