@@ -19,7 +19,9 @@
 //              the planar X buffer is the A operand as it stands -- no-swizzle K-major descriptor)
 //   warps 8-11 "drain": convolution columns TMEM -> shared memory as 16-channel planar chunks (the Z ring, two slots)
 //              ... and, two chunks later, "final": mixed chunk + residual columns (still in TMEM) + bias,
-//              PReLU, + embedding -> planar-4 global stores
+//              PReLU, + embedding -> planar-4 global stores; with VUP > 0 (production calls) the finished chunk goes back to
+//              shared memory instead and the same warps apply the up-path CNN_layer that follows the block (joint resample
+//              V -> VUP) and accumulate the result onto the U-Net skip tensor in place (red.global.add.v4.f32) -- see upsample()
 //   warps 0-3  T-mix  Y1[q,v,c] = sum_t Z[t,v,c] * Tm[v][t][q]      (register-resident weight slices, packed FFMA2)
 //   warps 4-7  A-mix  Y2[t,w,c] = sum_v Y1[t,v,c] * A[t][v][w]      -> planar fp32 chunk for the final stage
 // The convolution of tile i+1 (tensor pipe) overlaps the mixes of tile i (FMA pipe); TMEM holds two accumulator sets.
