@@ -57,6 +57,33 @@ def test_auc_with_the_frame_score_accelerator_is_bit_identical(golden, name):
     assert abs(auc1 - float(golden("postproc")[name])) < 1e-9
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_accelerated_first_stage_on_random_epochs(seed):
+    """Property: for random epochs (ragged persons per clip, clips without windows for some transformation, shuffled item
+    order, padding on / off) the accelerated path and the all-host path produce the same per-frame scores bit for bit."""
+    rng = np.random.default_rng(100 + seed)
+    ntr, L = int(rng.integers(1, 4)), int(rng.integers(2, 7))
+    gt = {(int(s), int(c)): (rng.random(int(rng.integers(30, 90))) < 0.3).astype(np.int64)
+          for s, c in zip(rng.integers(1, 4, size=5), rng.permutation(20)[:5])}
+    for g in gt.values():
+        g[0], g[-1] = 0, 1                                 # both classes present
+    items = []
+    for tr in range(ntr):
+        for (scene, clip), g in gt.items():
+            for person in rng.permutation(6)[: int(rng.integers(1, 4))]:
+                for _ in range(int(rng.integers(1, 12))):
+                    f0 = int(rng.integers(1, len(g) - L + 1))
+                    items.append((tr, scene, clip, int(person), f0))
+    order = rng.permutation(len(items))
+    items = [items[i] for i in order]
+    trans = np.array([i[0] for i in items]); meta = np.array([[i[1], i[2], i[3], i[4]] for i in items])
+    frames = np.array([np.arange(i[4], i[4] + L) for i in items]); out = rng.random(len(items)).astype(np.float32)
+    kw = dict(num_transform=ntr, pad_size=int(rng.choice([-1, 2, 5])), frames_shift=3, filter_kernel_size=4, return_scores=True)
+    a0, p0, g0 = postproc.dataset_auc(out, trans, meta, frames, gt, **kw)
+    a1, p1, g1 = postproc.dataset_auc(out, trans, meta, frames, gt, frame_scores=_frame_scores_host, **kw)
+    assert a0 == a1 and np.array_equal(p0, p1) and np.array_equal(g0, g1)
+
+
 def test_avenue_mask_lengths():
     m = postproc.avenue_hr_mask()
     assert {k: len(v) for k, v in m.items()} == {1: 1439, 2: 1211, 3: 923, 6: 1283, 16: 740}  # eval_utils.py:153-157
