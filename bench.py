@@ -478,14 +478,21 @@ def run_b200(a):
                   "note": "tcgen05.mma kind::tf32, three MMAs per fp32 product (hi*hi + hi*lo + lo*hi)"}
     # FMA-pipe view: only the position mixes run there in the tensor-core blocks (the 1x1 convolutions are on the tensor pipe)
     fma_flops_per_launch = top_flops_per_launch
+    fma_counts = "the T-mix and A-mix FMAs of the kernel (2*Cin*P*(T+V) per window); its convolution flops are under 'tensor'"
+    conv_first = {"st_gcnnsd3.1": 12, "st_gcnnsu4.1": 17}   # conv-first blocks: joints of the fused up-path CNN_layer's output
     if top["kernel"] in conv:
         ci, co, v = conv[top["kernel"]]
         fma_flops_per_launch = 2.0 * ci * T * v * (T + v) * windows_per_launch
+        if top["kernel"] in conv_first:   # mixes run on the Cout side there, plus the fused joint resample (V -> Vup) on the FMA pipe
+            vup = conv_first[top["kernel"]]
+            fma_flops_per_launch = (2.0 * co * T * v * (T + v) + 2.0 * co * T * v * vup) * windows_per_launch
+            fma_counts = ("conv-first block: T-mix and A-mix on the Cout side (2*Cout*P*(T+V) per window) + the fused joint resample "
+                          "(2*Cout*T*V*Vup); its convolution flops are under 'tensor'")
     fp32 = {"achieved_tflops": round(fma_flops_per_launch / top_sec_per_launch / 1e12, 2),
             "peak_tflops": round(fp32_peak, 2), "peak_source": "mcd_probe_fp32_detail: max of FFMA / FFMA2 register loops on this GPU",
             "probe_ffma_tflops": round(ffma_peak, 2), "probe_ffma2_tflops": round(ffma2_peak, 2),
             "frac": round(fma_flops_per_launch / top_sec_per_launch / 1e12 / fp32_peak, 4),
-            "counts": "the T-mix and A-mix FMAs of the kernel (2*Cin*P*(T+V) per window); its convolution flops are under 'tensor'",
+            "counts": fma_counts,
             "algorithmic_tflops_all_pipes": round(top_flops_per_launch / top_sec_per_launch / 1e12, 2),
             "whole_step_tflops": round(B * G * (N - 1) * unet_flops / (ms * 1e-3) / 1e12, 2)}
     hbm = {"achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4)}
