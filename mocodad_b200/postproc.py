@@ -125,7 +125,7 @@ def dataset_auc(out: np.ndarray, trans: np.ndarray, meta: np.ndarray, frames: np
     bounds = np.concatenate([[0], np.flatnonzero(np.any(key[1:] != key[:-1], axis=1)) + 1, [len(key)]]).astype(np.int64)
     groups = {tuple(key[b].tolist()): (int(b), int(e)) for b, e in zip(bounds[:-1], bounds[1:]) if e > b}
     rows_of, row_scores = {}, None
-    if frame_scores is not None and len(out):
+    if frame_scores is not None and len(out) and out.dtype == np.float32:   # (other dtypes: the all-host path keeps them exact)
         # one output row per (transformation, scene, clip, person) of a clip that has ground truth: consecutive in the sorted order
         pkey = np.concatenate([key, meta[:, 2:3].astype(np.int64)], axis=1)
         pb = np.concatenate([[0], np.flatnonzero(np.any(pkey[1:] != pkey[:-1], axis=1)) + 1, [len(pkey)]]).astype(np.int64)
